@@ -1,0 +1,492 @@
+// cudart_b200/csrc/crt_api.cu - the C ABI of include/crt_abi.h: context, scene upload, wave scheduling.
+//
+// A context owns (on one device): the re-flattened scene, the wavefront buffers sized for
+// spp_per_wave x owned pixels paths, the compact float4 accumulator of the owned row tiles, and one
+// stream.  crt_render() enqueues, per wave, raygen -> [extend, shade, shadow] x 6 -> accumulate; queue
+// sizes never come back to the host, so a whole render is a fixed launch sequence with no host syncs.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/crt_abi.h"
+#include "host_scene.h"
+#include "kernels.cuh"
+
+using namespace crt;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(CRT_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        n = count;
+        return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; }
+};
+
+}  // namespace
+
+struct crt_ctx {
+    int device = 0;
+    bool own_stream = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;   // render spans not yet folded into render_ms
+    LaunchCfg cfg{};
+    uint32_t flags = 0, seed = 1234, spp_per_wave = 1, samples = 0;
+    DScene sc{};
+    DTiling tl{};
+    DWave wv{};
+    WideStats wide_stats{};
+    // scene
+    DevBuf<float4> wide, tri_isect, tri_shade, mats;
+    DevBuf<uint32_t> lights, tex_dims, tex_offsets;
+    DevBuf<float> tex_data;
+    // wave
+    DevBuf<float4> rq_o[2], rq_d[2], hits, sq_o, sq_d, sq_c, st_mask, color;
+    DevBuf<uint32_t> rq_path[2], sq_path, st_key;
+    DevBuf<DCounters> counters;
+    DevBuf<DStats> stats;
+    DevBuf<float4> accum;
+    DevBuf<uint8_t> gamma_lut;
+    // scratch for resolve / trace
+    DevBuf<uchar4> rgba;
+    DevBuf<float> f32;
+    DevBuf<uint32_t> head;
+    uint64_t launches = 0;
+    double render_ms = 0;
+    double stage_ms[CRT_STAGE_COUNT] = {0};
+};
+
+namespace {
+
+template <typename T>
+int upload(DevBuf<T>& b, const void* src, size_t count, cudaStream_t s) {
+    CU(b.alloc(count));
+    if (count) CU(cudaMemcpyAsync(b.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    return CRT_OK;
+}
+
+void free_all(crt_ctx* c) {
+    cudaSetDevice(c->device);
+    c->wide.release(); c->tri_isect.release(); c->tri_shade.release(); c->mats.release();
+    c->lights.release(); c->tex_dims.release(); c->tex_offsets.release(); c->tex_data.release();
+    for (int i = 0; i < 2; i++) { c->rq_o[i].release(); c->rq_d[i].release(); c->rq_path[i].release(); }
+    c->hits.release(); c->sq_o.release(); c->sq_d.release(); c->sq_c.release(); c->st_mask.release(); c->color.release();
+    c->sq_path.release(); c->st_key.release(); c->counters.release(); c->stats.release(); c->accum.release();
+    c->gamma_lut.release(); c->rgba.release(); c->f32.release(); c->head.release();
+    for (auto& pr : c->pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+}
+
+int check_kernel(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CRT_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+    return CRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int crt_abi_version(void) { return CRT_ABI_VERSION; }
+const char* crt_last_error(void) { return g_err.c_str(); }
+
+int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_options* opt, crt_ctx** out) {
+    if (!s || !out || !W || !H) return fail(CRT_ERR_INVALID, "crt_create: null scene/out or empty image");
+    if (!s->tris || !s->nodes || !s->n_tris || !s->n_nodes || !s->camera) return fail(CRT_ERR_INVALID, "crt_create: empty scene");
+    if (s->n_mats > 128) return fail(CRT_ERR_LIMIT, "crt_create: %u materials > MAX_MATERIALS 128 (renderer.h:22)", s->n_mats);
+    if (s->n_tris >= kMaxTris) return fail(CRT_ERR_LIMIT, "crt_create: %u triangles >= %u", s->n_tris, kMaxTris);
+    if ((uint64_t)W * H >= (1ull << 31)) return fail(CRT_ERR_LIMIT, "crt_create: image too large");
+    crt_options o;
+    memset(&o, 0, sizeof o);
+    o.device = -1;
+    if (opt) memcpy(&o, opt, std::min<size_t>(opt->struct_size ? opt->struct_size : sizeof o, sizeof o));
+    if (o.world == 0) o.world = 1;
+    if (o.rank >= o.world) return fail(CRT_ERR_INVALID, "crt_create: rank %u >= world %u", o.rank, o.world);
+    if (o.tile_rows == 0) o.tile_rows = 8;
+    if (o.seed == 0) o.seed = 1234;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CRT_ERR_CUDA, "crt_create: no CUDA device (%s); this path has no CPU fallback", cudaGetErrorString(e));
+    int dev = o.device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(CRT_ERR_INVALID, "crt_create: device %d of %d", dev, ndev);
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail(CRT_ERR_CUDA, "crt_create: device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+
+    crt_ctx* c = new (std::nothrow) crt_ctx();
+    if (!c) return fail(CRT_ERR_NOMEM, "crt_create: out of host memory");
+    c->device = dev;
+    c->flags = o.flags;
+    c->seed = o.seed;
+    auto bail = [&](int code) { free_all(c); delete c; return code; };
+    if (o.stream) c->stream = (cudaStream_t)o.stream;
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(CRT_ERR_CUDA, "cudaStreamCreate failed"));
+        c->own_stream = true;
+    }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    c->cfg.sms = prop.multiProcessorCount;
+    c->cfg.stream = c->stream;
+
+    // ---- scene: re-flatten on the host, upload ----
+    const RefTriangle* tris = (const RefTriangle*)s->tris;
+    const RefNode* nodes = (const RefNode*)s->nodes;
+    for (uint32_t k = 0; k < s->n_nodes; k++) {
+        const RefNode& nd = nodes[k];
+        bool ok = nd.nTris > 0 ? ((uint32_t)nd.offset + (uint32_t)nd.nTris <= s->n_tris)
+                               : (nd.offset > (int32_t)k && (uint32_t)nd.offset < s->n_nodes && k + 1 < s->n_nodes);
+        if (!ok) return bail(fail(CRT_ERR_INVALID, "crt_create: BVH node %u is malformed", k));
+    }
+    for (uint32_t k = 0; k < s->n_lights; k++)
+        if (s->light_indices[k] >= s->n_tris) return bail(fail(CRT_ERR_INVALID, "crt_create: light index out of range"));
+    std::vector<WideNode> wide;
+    c->wide_stats = flatten_wide(nodes, s->n_nodes, wide);
+    if (3 * c->wide_stats.depth + 4 > 64) return bail(fail(CRT_ERR_LIMIT, "crt_create: wide BVH depth %u exceeds the traversal stack", c->wide_stats.depth));
+    std::vector<TriIsect> isect;
+    std::vector<TriShade> shade;
+    make_tri_records(tris, s->n_tris, nodes, s->n_nodes, isect, shade);
+    for (uint32_t i = 0; i < s->n_tris; i++)
+        if (tris[i].materialId >= std::max(s->n_mats, 1u)) return bail(fail(CRT_ERR_INVALID, "crt_create: triangle %u has material %u of %u", i, tris[i].materialId, s->n_mats));
+    std::vector<float4> mats(4 * (size_t)std::max(s->n_mats, 1u));
+    for (uint32_t m = 0; m < s->n_mats; m++) {
+        const float* f = s->mat_floats + 12 * (size_t)m;
+        float bs, tx;
+        memcpy(&bs, &s->mat_indices[2 * m], 4);
+        memcpy(&tx, &s->mat_indices[2 * m + 1], 4);
+        if (s->mat_indices[2 * m + 1] >= (int32_t)s->n_tex) return bail(fail(CRT_ERR_INVALID, "crt_create: material %u texture index out of range", m));
+        mats[4 * m + 0] = make_float4(f[0], f[1], f[2], bs);
+        mats[4 * m + 1] = make_float4(f[3], f[4], f[5], tx);
+        mats[4 * m + 2] = make_float4(f[6], f[7], f[8], 0.f);
+        mats[4 * m + 3] = make_float4(f[9], f[10], f[11], 0.f);
+    }
+    int rc;
+#define UP(buf, src, count) if ((rc = upload(c->buf, src, count, c->stream)) != CRT_OK) return bail(rc)
+    UP(wide, wide.data(), wide.size() * 8);
+    UP(tri_isect, isect.data(), isect.size() * 3);
+    UP(tri_shade, shade.data(), shade.size() * 5);
+    UP(mats, mats.data(), mats.size());
+    UP(lights, s->light_indices, s->n_lights);
+    UP(tex_dims, s->tex_dims, 2 * (size_t)s->n_tex);
+    UP(tex_offsets, s->tex_offsets, s->n_tex ? s->n_tex + 1 : 0);
+    UP(tex_data, s->tex_data, 3 * (size_t)s->tex_texels);
+    uint8_t lut[256];
+    {   // gammaCorrectPixel (renderer.cu:495-504) tabulated with the host's powf, i.e. the reference's own libm
+        const float invGamma = 1.f / 2.2f;
+        for (int v = 0; v < 256; v++) lut[v] = (unsigned char)(powf((float)v * 1.f / 255.f, invGamma) * 255.f);
+    }
+    UP(gamma_lut, lut, 256);
+#undef UP
+    DScene& sc = c->sc;
+    sc.wide = c->wide.p; sc.tri_isect = c->tri_isect.p; sc.tri_shade = c->tri_shade.p; sc.mats = c->mats.p;
+    sc.lights = c->lights.p; sc.tex_data = c->tex_data.p; sc.tex_dims = c->tex_dims.p; sc.tex_offsets = c->tex_offsets.p;
+    sc.n_wide = (uint32_t)wide.size(); sc.n_tris = s->n_tris; sc.n_mats = s->n_mats; sc.n_lights = s->n_lights;
+    sc.n_tex = s->n_tex; sc.tex_texels = s->tex_texels; sc.lights_area = s->lights_area;
+    memcpy(&sc.cam, s->camera, sizeof(RefCamera));
+    sc.cam.xpixels = (int32_t)W;
+    sc.cam.ypixels = (int32_t)H;
+    {   // culling margins, relative to the scene's extent (DESIGN.md "distance culling")
+        const RefNode& r = nodes[0];
+        float dx = r.mx.x - r.mn.x, dy = r.mx.y - r.mn.y, dz = r.mx.z - r.mn.z;
+        float diag = sqrtf(dx * dx + dy * dy + dz * dz);
+        if (!(diag > 0.f) || !std::isfinite(diag)) diag = 1.f;
+        sc.cull_far_rel = 1.02f;
+        sc.cull_far_abs = 1e-3f * diag;
+        sc.cull_behind = -2e-2f * diag;
+    }
+
+    // ---- pixel ownership ----
+    DTiling& tl = c->tl;
+    tl.W = W; tl.H = H; tl.rank = o.rank; tl.world = o.world; tl.tile_rows = o.tile_rows;
+    const uint32_t n_tiles = (H + o.tile_rows - 1) / o.tile_rows;
+    uint32_t rows = 0;
+    for (uint32_t t = o.rank; t < n_tiles; t += o.world) rows += std::min(o.tile_rows, H - t * o.tile_rows);
+    tl.local_rows = rows;
+    tl.local_pixels = rows * W;
+    tl.padded_pixels = ((n_tiles + o.world - 1) / o.world) * o.tile_rows * W;
+
+    // ---- wave buffers ----
+    uint32_t k = o.spp_per_wave;
+    if (k == 0) {       // auto: about 4M paths in flight, at least 1 spp
+        k = (uint32_t)std::max<uint64_t>(1, (4ull << 20) / std::max<uint32_t>(tl.local_pixels, 1));
+        k = std::min<uint32_t>(k, 16);
+    }
+    c->spp_per_wave = k;
+    const size_t cap = std::max<size_t>((size_t)tl.local_pixels * k, 32);
+    if (cap >= (1ull << 31)) return bail(fail(CRT_ERR_LIMIT, "crt_create: %zu paths per wave", cap));
+#define AL(buf, count) if (c->buf.alloc(count) != cudaSuccess) return bail(fail(CRT_ERR_NOMEM, "crt_create: cudaMalloc(%s) failed: %s", #buf, cudaGetErrorString(cudaGetLastError())))
+    for (int i = 0; i < 2; i++) { AL(rq_o[i], cap); AL(rq_d[i], cap); AL(rq_path[i], cap); }
+    AL(hits, cap); AL(sq_o, cap); AL(sq_d, cap); AL(sq_c, cap); AL(sq_path, cap);
+    AL(st_mask, cap); AL(st_key, cap); AL(color, cap);
+    AL(counters, 1); AL(stats, 1); AL(head, 1);
+    AL(accum, tl.padded_pixels);
+#undef AL
+    DWave& wv = c->wv;
+    for (int i = 0; i < 2; i++) { wv.rq_o[i] = c->rq_o[i].p; wv.rq_d[i] = c->rq_d[i].p; wv.rq_path[i] = c->rq_path[i].p; }
+    wv.hits = c->hits.p; wv.sq_o = c->sq_o.p; wv.sq_d = c->sq_d.p; wv.sq_c = c->sq_c.p; wv.sq_path = c->sq_path.p;
+    wv.st_mask = c->st_mask.p; wv.st_key = c->st_key.p; wv.color = c->color.p;
+    wv.counters = c->counters.p; wv.stats = c->stats.p; wv.capacity = (uint32_t)cap;
+    if (cudaMemsetAsync(c->accum.p, 0, (size_t)tl.padded_pixels * sizeof(float4), c->stream) != cudaSuccess ||
+        cudaMemsetAsync(c->stats.p, 0, sizeof(DStats), c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess)
+        return bail(fail(CRT_ERR_CUDA, "crt_create: upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = c;
+    return CRT_OK;
+}
+
+void crt_destroy(crt_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_all(c);
+    delete c;
+}
+
+int crt_render(crt_ctx* c, uint32_t spp) {
+    if (!c) return fail(CRT_ERR_INVALID, "crt_render: null ctx");
+    CU(cudaSetDevice(c->device));
+    const bool exact = c->flags & CRT_FLAG_EXACT_VISIT, prof = c->flags & CRT_FLAG_PROFILE, stats = c->flags & CRT_FLAG_STATS;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, c->stream));
+    struct Span { int stage; cudaEvent_t e; };
+    std::vector<Span> spans;        // CRT_FLAG_PROFILE: an event after every launch; stage -1 opens a wave
+    auto mark = [&](int stage) {
+        if (!prof) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, c->stream);
+        spans.push_back({stage, e});
+    };
+    uint32_t done = 0;
+    while (done < spp && c->tl.local_pixels) {
+        const uint32_t k = std::min(c->spp_per_wave, spp - done);
+        CU(cudaMemsetAsync(c->counters.p, 0, sizeof(DCounters), c->stream));
+        mark(-1);
+        launch_raygen(c->sc, c->tl, c->wv, c->samples + done, k, c->seed, c->cfg);
+        mark(CRT_STAGE_RAYGEN);
+        for (int bounce = 0; bounce < kMaxBounces; bounce++) {
+            launch_extend(c->sc, c->wv, bounce, exact, stats, c->cfg);
+            mark(CRT_STAGE_EXTEND);
+            launch_shade(c->sc, c->tl, c->wv, bounce, c->cfg);
+            mark(CRT_STAGE_SHADE);
+            launch_shadow(c->sc, c->wv, bounce, exact, stats, c->cfg);
+            mark(CRT_STAGE_SHADOW);
+        }
+        launch_accumulate(c->tl, c->wv, c->accum.p, k, c->cfg);
+        mark(CRT_STAGE_ACCUM);
+        c->launches += 2 + 3 * kMaxBounces;
+        done += k;
+    }
+    CU(cudaEventRecord(b, c->stream));
+    c->pending.emplace_back(a, b);
+    c->samples += spp;
+    int rc = check_kernel("render wave");
+    if (rc) return rc;
+    if (prof) {
+        CU(cudaStreamSynchronize(c->stream));
+        for (size_t i = 1; i < spans.size(); i++) {
+            if (spans[i].stage < 0) continue;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, spans[i - 1].e, spans[i].e);
+            c->stage_ms[spans[i].stage] += ms;
+        }
+        for (auto& sp : spans) cudaEventDestroy(sp.e);
+    }
+    return CRT_OK;
+}
+
+int crt_sync(crt_ctx* c) {
+    if (!c) return fail(CRT_ERR_INVALID, "crt_sync: null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto& pr : c->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) c->render_ms += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    c->pending.clear();
+    return CRT_OK;
+}
+
+uint32_t crt_samples_rendered(const crt_ctx* c) { return c ? c->samples : 0; }
+
+static int resolve_common(crt_ctx* c, const float4* src, bool gathered, uint8_t* rgba_dst, float* f32_dst, int f32_mode) {
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->tl.W * c->tl.H;
+    if (rgba_dst && !c->rgba.p) CU(c->rgba.alloc(n));
+    if (f32_dst && !c->f32.p) CU(c->f32.alloc(3 * n));
+    if (rgba_dst) CU(cudaMemsetAsync(c->rgba.p, 0, n * 4, c->stream));
+    if (f32_dst) CU(cudaMemsetAsync(c->f32.p, 0, 3 * n * sizeof(float), c->stream));
+    launch_resolve(c->tl, src, gathered, std::max(c->samples, 1u), c->gamma_lut.p, rgba_dst ? c->rgba.p : nullptr,
+                   f32_dst ? c->f32.p : nullptr, f32_mode, c->cfg);
+    c->launches++;
+    int rc = check_kernel("resolve");
+    if (rc) return rc;
+    if (rgba_dst) CU(cudaMemcpyAsync(rgba_dst, c->rgba.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (f32_dst) CU(cudaMemcpyAsync(f32_dst, c->f32.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    return crt_sync(c);
+}
+
+int crt_resolve_rgba8(crt_ctx* c, uint8_t* dst) {
+    if (!c || !dst) return fail(CRT_ERR_INVALID, "crt_resolve_rgba8: null argument");
+    return resolve_common(c, c->accum.p, false, dst, nullptr, 0);
+}
+int crt_resolve_f32(crt_ctx* c, float* dst) {
+    if (!c || !dst) return fail(CRT_ERR_INVALID, "crt_resolve_f32: null argument");
+    return resolve_common(c, c->accum.p, false, nullptr, dst, 1);
+}
+int crt_read_accum(crt_ctx* c, float* dst) {
+    if (!c || !dst) return fail(CRT_ERR_INVALID, "crt_read_accum: null argument");
+    return resolve_common(c, c->accum.p, false, nullptr, dst, 2);
+}
+int crt_resolve_gathered(crt_ctx* c, const void* d_gathered, uint8_t* rgba8_dst, float* f32_dst) {
+    if (!c || !d_gathered) return fail(CRT_ERR_INVALID, "crt_resolve_gathered: null argument");
+    return resolve_common(c, (const float4*)d_gathered, true, rgba8_dst, f32_dst, 1);
+}
+
+int crt_reset(crt_ctx* c) {
+    if (!c) return fail(CRT_ERR_INVALID, "crt_reset: null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->accum.p, 0, (size_t)c->tl.padded_pixels * sizeof(float4), c->stream));
+    c->samples = 0;
+    return CRT_OK;
+}
+
+int crt_get_counters(crt_ctx* c, crt_counters* out) {
+    if (!c || !out) return fail(CRT_ERR_INVALID, "crt_get_counters: null argument");
+    int rc = crt_sync(c);
+    if (rc) return rc;
+    DStats st;
+    CU(cudaMemcpy(&st, c->stats.p, sizeof st, cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof *out);
+    out->samples = st.samples; out->extend_rays = st.extend_rays; out->shadow_rays = st.shadow_rays;
+    out->node_visits = st.node_visits; out->tri_tests = st.tri_tests;
+    out->kernel_launches = c->launches;
+    out->render_ms = c->render_ms;
+    for (int i = 0; i < CRT_STAGE_COUNT; i++) out->stage_ms[i] = c->stage_ms[i];
+    return CRT_OK;
+}
+
+int crt_trace_closest_device(crt_ctx* c, const void* d_rays, size_t n, void* d_hits, uint32_t flags, float* kernel_ms) {
+    if (!c || (n && (!d_rays || !d_hits))) return fail(CRT_ERR_INVALID, "crt_trace_closest_device: null argument");
+    if (n >= (1ull << 31)) return fail(CRT_ERR_LIMIT, "crt_trace_closest_device: too many rays");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->head.p, 0, sizeof(uint32_t), c->stream));
+    CU(cudaEventRecord(c->ev0, c->stream));
+    launch_trace(c->sc, (const float4*)d_rays, (uint32_t)n, (float4*)d_hits, c->head.p, c->stats.p,
+                 flags & CRT_FLAG_EXACT_VISIT, (flags | c->flags) & CRT_FLAG_STATS, c->cfg);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->launches++;
+    int rc = check_kernel("trace");
+    if (rc) return rc;
+    if (kernel_ms) {
+        CU(cudaEventSynchronize(c->ev1));
+        CU(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
+    }
+    return CRT_OK;
+}
+
+int crt_trace_closest(crt_ctx* c, const crt_ray* rays, size_t n, crt_hit* hits, uint32_t flags) {
+    if (!c || (n && (!rays || !hits))) return fail(CRT_ERR_INVALID, "crt_trace_closest: null argument");
+    if (n == 0) return CRT_OK;
+    CU(cudaSetDevice(c->device));
+    DevBuf<float4> dr, dh;
+    CU(dr.alloc(2 * n));
+    if (dh.alloc(n) != cudaSuccess) { dr.release(); return fail(CRT_ERR_NOMEM, "crt_trace_closest: cudaMalloc failed"); }
+    int rc = CRT_OK;
+    if (cudaMemcpyAsync(dr.p, rays, n * sizeof(crt_ray), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+        rc = fail(CRT_ERR_CUDA, "crt_trace_closest: H2D failed");
+    if (!rc) rc = crt_trace_closest_device(c, dr.p, n, dh.p, flags, nullptr);
+    if (!rc && cudaMemcpyAsync(hits, dh.p, n * sizeof(crt_hit), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        rc = fail(CRT_ERR_CUDA, "crt_trace_closest: D2H failed");
+    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess)
+        rc = fail(CRT_ERR_CUDA, "crt_trace_closest: %s", cudaGetErrorString(cudaGetLastError()));
+    dr.release();
+    dh.release();
+    return rc;
+}
+
+int crt_accum_device_ptr(crt_ctx* c, void** d_ptr, size_t* padded_pixels) {
+    if (!c || !d_ptr) return fail(CRT_ERR_INVALID, "crt_accum_device_ptr: null argument");
+    *d_ptr = c->accum.p;
+    if (padded_pixels) *padded_pixels = c->tl.padded_pixels;
+    return CRT_OK;
+}
+
+// ---- host scene build ----------------------------------------------------------------------------
+int crt_build_bvh(void* tris, const float* positions, uint32_t n_tris, void* nodes_out, uint32_t* n_nodes_out) {
+    if (!tris || !positions || !nodes_out || !n_nodes_out) return fail(CRT_ERR_INVALID, "crt_build_bvh: null argument");
+    try {
+        std::vector<RefNode> nodes;
+        build_reference_bvh((RefTriangle*)tris, positions, n_tris, nodes);
+        memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(RefNode));
+        *n_nodes_out = (uint32_t)nodes.size();
+    } catch (const std::bad_alloc&) {
+        return fail(CRT_ERR_NOMEM, "crt_build_bvh: out of memory");
+    }
+    return CRT_OK;
+}
+
+int crt_build_lights(void* tris, uint32_t n_tris, float* mat_floats, const int32_t* mat_indices, uint32_t n_mats,
+                     uint32_t* light_indices_out, uint32_t* n_lights_out, float* lights_area_out) {
+    if (!tris || !mat_floats || !mat_indices || !light_indices_out || !n_lights_out || !lights_area_out)
+        return fail(CRT_ERR_INVALID, "crt_build_lights: null argument");
+    std::vector<uint32_t> lights;
+    float area = 0;
+    build_light_list((RefTriangle*)tris, n_tris, mat_floats, mat_indices, n_mats, lights, area);
+    memcpy(light_indices_out, lights.data(), lights.size() * 4);
+    *n_lights_out = (uint32_t)lights.size();
+    *lights_area_out = area;
+    return CRT_OK;
+}
+
+int crt_wide_bvh(const void* nodes, uint32_t n_nodes, void* wide_out, uint32_t cap, uint32_t* n_wide_out) {
+    if (!nodes || !n_wide_out) return fail(CRT_ERR_INVALID, "crt_wide_bvh: null argument");
+    std::vector<WideNode> wide;
+    flatten_wide((const RefNode*)nodes, n_nodes, wide);
+    *n_wide_out = (uint32_t)wide.size();
+    if (wide_out) memcpy(wide_out, wide.data(), std::min<size_t>(cap, wide.size()) * sizeof(WideNode));
+    return CRT_OK;
+}
+
+}  // extern "C"

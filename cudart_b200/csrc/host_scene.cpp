@@ -1,0 +1,351 @@
+// cudart_b200/csrc/host_scene.cpp - host scene preparation (no CUDA).
+//
+// build_reference_bvh() rebuilds the tree of the reference's constructBVH (bvh.cpp:65-323) bit for
+// bit, with the reference's undefined behaviour pinned the way SURVEY.md D1 defines it: every float3
+// the reference reads uninitialised (centroid bounds bvh.cpp:133, bucket bounds :205, the four split
+// bounds :231) starts at (0,0,0).  The quirks that shape the tree are kept on purpose:
+//   - "surface area" is the box VOLUME dx*dy*dz (bvh.cpp:334-337, D2), NaN costs included;
+//   - the lower partition [start,mid) is built (and its triangles emitted) BEFORE the upper one, yet
+//     the upper one becomes child 0 / index+1 in the flattened array (bvh.cpp:302-304 under g++'s
+//     right-to-left argument evaluation, D3) - spelled out here instead of relying on evaluation order;
+//   - only leaves copy splitAxis, and a leaf's is 0, so every flattened node has axis 0 (D4);
+//   - the permutation comes from libstdc++'s std::partition / std::nth_element / std::min_element
+//     applied to a contiguous array with the reference's predicates (D26).
+// tests/test_bvh_build.py compares the result node by node with the reference's own dump.
+#include "host_scene.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cstring>
+
+namespace crt {
+namespace {
+
+inline F3 lo3(const F3& a, const F3& b) { return {a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y, a.z < b.z ? a.z : b.z}; }
+inline F3 hi3(const F3& a, const F3& b) { return {a.x > b.x ? a.x : b.x, a.y > b.y ? a.y : b.y, a.z > b.z ? a.z : b.z}; }
+inline float axis_of(const F3& v, int d) { return d == 0 ? v.x : (d == 1 ? v.y : v.z); }
+
+struct PrimBox {          // bvh.cpp:18-30
+    int tri;
+    F3 mn, mx, center;
+};
+
+struct BuildNode {
+    F3 mn, mx;
+    int child0 = -1, child1 = -1;       // child0 = upper partition [mid,end), child1 = lower [start,mid)
+    uint32_t first = 0, count = 0;      // leaf payload
+};
+
+struct Builder {
+    const RefTriangle* src;
+    std::vector<PrimBox> prims;
+    std::vector<RefTriangle> ordered;
+    std::vector<BuildNode> pool;
+
+    // "volume as area" (bvh.cpp:334-337)
+    static float box_measure(const F3& mn, const F3& mx) {
+        F3 d{mx.x - mn.x, mx.y - mn.y, mx.z - mn.z};
+        return d.x * d.y * d.z;
+    }
+    // bvh.cpp:339-346
+    static int widest_axis(const F3& mn, const F3& mx) {
+        F3 d{mx.x - mn.x, mx.y - mn.y, mx.z - mn.z};
+        if (d.x > d.y && d.x > d.z) return 0;
+        if (d.y > d.z) return 1;
+        return 2;
+    }
+    // bvh.cpp:326-332 followed by the int truncation and the 8 -> 7 clamp of :211-223
+    static int bucket_of(const F3& cmin, const F3& cmax, const F3& p, int dim) {
+        constexpr int kBuckets = 8;
+        F3 r{p.x - cmin.x, p.y - cmin.y, p.z - cmin.z};
+        if (cmax.x > cmin.x) r.x /= (cmax.x - cmin.x);
+        if (cmax.y > cmin.y) r.y /= (cmax.y - cmin.y);
+        if (cmax.z > cmin.z) r.z /= (cmax.z - cmin.z);
+        int b = kBuckets * axis_of(r, dim);
+        if (b == kBuckets) b = kBuckets - 1;
+        return b;
+    }
+
+    int emit_leaf(int node, uint32_t start, uint32_t end, const F3& mn, const F3& mx) {
+        BuildNode& nd = pool[node];
+        nd.first = (uint32_t)ordered.size();
+        nd.count = end - start;
+        nd.mn = mn;
+        nd.mx = mx;
+        for (uint32_t i = start; i < end; i++) ordered.push_back(src[prims[i].tri]);
+        return node;
+    }
+
+    void median_split(uint32_t start, uint32_t mid, uint32_t end, int dim) {
+        PrimBox* base = prims.data();
+        std::nth_element(base + start, base + mid, base + end,
+                         [dim](const PrimBox& a, const PrimBox& b) { return axis_of(a.center, dim) < axis_of(b.center, dim); });
+    }
+
+    int build(uint32_t start, uint32_t end) {
+        int node = (int)pool.size();
+        pool.emplace_back();
+        F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (uint32_t i = start; i < end; i++) {
+            mn = lo3(mn, prims[i].mn);
+            mx = hi3(mx, prims[i].mx);
+        }
+        uint32_t n = end - start;
+        if (n <= 3) return emit_leaf(node, start, end, mn, mx);
+
+        F3 cmin{0.f, 0.f, 0.f}, cmax{0.f, 0.f, 0.f};          // pinned zero start (D1)
+        for (uint32_t i = start; i < end; i++) {
+            cmin = lo3(cmin, prims[i].center);
+            cmax = hi3(cmax, prims[i].center);
+        }
+        int dim = widest_axis(cmin, cmax);
+        if (axis_of(cmax, dim) == axis_of(cmin, dim)) return emit_leaf(node, start, end, mn, mx);
+
+        uint32_t mid = (start + end) / 2;
+        if (n <= 4) {
+            median_split(start, mid, end, dim);
+        } else {
+            constexpr int kBuckets = 8;
+            struct Bucket { int count = 0; F3 mn{0.f, 0.f, 0.f}, mx{0.f, 0.f, 0.f}; } buckets[kBuckets];   // zero start (D1)
+            for (uint32_t i = start; i < end; i++) {
+                int b = bucket_of(cmin, cmax, prims[i].center, dim);
+                buckets[b].count++;
+                buckets[b].mn = lo3(buckets[b].mn, prims[i].mn);
+                buckets[b].mx = hi3(buckets[b].mx, prims[i].mx);
+            }
+            float cost[kBuckets - 1];
+            for (int i = 0; i < kBuckets - 1; i++) {
+                F3 amn{0.f, 0.f, 0.f}, amx{0.f, 0.f, 0.f}, bmn{0.f, 0.f, 0.f}, bmx{0.f, 0.f, 0.f};     // zero start (D1)
+                int ca = 0, cb = 0;
+                for (int j = 0; j <= i; j++) {
+                    amn = lo3(amn, buckets[j].mn);
+                    amx = hi3(amx, buckets[j].mx);
+                    ca += buckets[j].count;
+                }
+                for (int j = i + 1; j < kBuckets; j++) {
+                    bmn = lo3(bmn, buckets[j].mn);
+                    bmx = hi3(bmx, buckets[j].mx);
+                    cb += buckets[j].count;
+                }
+                cost[i] = 1.f + (ca * box_measure(amn, amx) + cb * box_measure(bmn, bmx)) / box_measure(mn, mx);
+            }
+            int split = (int)(std::min_element(cost, cost + (kBuckets - 1)) - cost);
+            // n > 4 > maxTrisInNode, so the reference always splits here (bvh.cpp:252, D5).
+            PrimBox* base = prims.data();
+            PrimBox* pm = std::partition(base + start, base + end, [=](const PrimBox& t) {
+                return bucket_of(cmin, cmax, t.center, dim) <= split;
+            });
+            mid = (uint32_t)(pm - base);
+            if (mid == start || mid == end) {
+                mid = (start + end) / 2;
+                median_split(start, mid, end, dim);
+            }
+        }
+        int lower = build(start, mid);      // built and emitted FIRST (D3) ...
+        int upper = build(mid, end);
+        BuildNode& nd = pool[node];
+        nd.child0 = upper;                  // ... but stored second: child 0 is the upper partition
+        nd.child1 = lower;
+        nd.mx = hi3(pool[upper].mx, pool[lower].mx);
+        nd.mn = lo3(pool[upper].mn, pool[lower].mn);
+        return node;
+    }
+
+    int flatten(int node, std::vector<RefNode>& out) {
+        int my = (int)out.size();
+        out.emplace_back();
+        std::memset(&out[my], 0, sizeof(RefNode));
+        out[my].mn = pool[node].mn;
+        out[my].mx = pool[node].mx;
+        if (pool[node].count > 0) {
+            out[my].offset = (int32_t)pool[node].first;
+            out[my].nTris = (int16_t)pool[node].count;
+            out[my].axis = 0;
+        } else {
+            flatten(pool[node].child0, out);
+            int second = flatten(pool[node].child1, out);
+            out[my].offset = second;
+        }
+        return my;
+    }
+};
+
+}  // namespace
+
+void build_reference_bvh(RefTriangle* tris, const float* positions, uint32_t n, std::vector<RefNode>& nodes_out) {
+    Builder b;
+    b.src = tris;
+    b.prims.reserve(n);
+    b.ordered.reserve(n);
+    for (uint32_t i = 0; i < n; i++) {            // bvh.cpp:79-96 (boxes from the three vertex positions)
+        const float* p = positions + 9 * (size_t)i;
+        F3 a{p[0], p[1], p[2]}, c{p[3], p[4], p[5]}, d{p[6], p[7], p[8]};
+        PrimBox pb;
+        pb.tri = (int)i;
+        pb.mn = {std::min(a.x, std::min(c.x, d.x)), std::min(a.y, std::min(c.y, d.y)), std::min(a.z, std::min(c.z, d.z))};
+        pb.mx = {std::max(a.x, std::max(c.x, d.x)), std::max(a.y, std::max(c.y, d.y)), std::max(a.z, std::max(c.z, d.z))};
+        pb.center = {(pb.mn.x + pb.mx.x) * 0.5f, (pb.mn.y + pb.mx.y) * 0.5f, (pb.mn.z + pb.mx.z) * 0.5f};
+        b.prims.push_back(pb);
+    }
+    nodes_out.clear();
+    if (n == 0) return;
+    b.pool.reserve(2 * (size_t)n);
+    int root = b.build(0, n);
+    nodes_out.reserve(b.pool.size());
+    b.flatten(root, nodes_out);
+    std::copy(b.ordered.begin(), b.ordered.end(), tris);
+}
+
+void build_light_list(RefTriangle* tris, uint32_t n, float* mat_floats, const int32_t* mat_indices, uint32_t n_mats,
+                      std::vector<uint32_t>& lights, float& lights_area) {
+    constexpr int kEmissive = 5;                 // refl_t EMISSIVE (material.h:8-15)
+    lights.clear();
+    float area = 0;
+    for (uint32_t i = 0; i < n; i++) {           // scene.cpp:148-158
+        uint32_t m = tris[i].materialId;
+        if (m < n_mats && mat_indices[2 * m] == kEmissive) {
+            tris[i].triId = i;
+            lights.push_back(i);
+            area += tris[i].area;                // Scene::getLightsSurfaceArea, same summation order
+        }
+    }
+    lights_area = area;
+    for (uint32_t m = 0; m < n_mats; m++)        // scene.cpp:161-164: ka *= total light area
+        for (int k = 0; k < 3; k++) mat_floats[12 * m + 3 + k] = mat_floats[12 * m + 3 + k] * area;
+}
+
+// ---- wide re-flattening -----------------------------------------------------------------------
+namespace {
+inline float half_area(const RefNode& n) {
+    float dx = n.mx.x - n.mn.x, dy = n.mx.y - n.mn.y, dz = n.mx.z - n.mn.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+}  // namespace
+
+WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, std::vector<WideNode>& out) {
+    WideStats st;
+    out.clear();
+    if (n_nodes == 0) return st;
+    struct Item { uint32_t bin; uint32_t wide; uint32_t depth; };
+    std::vector<Item> todo;
+
+    // A slot is either a binary node index or (for chunks of an oversized reference leaf) an explicit range.
+    struct Slot { uint32_t bin; uint32_t first, count; bool chunk; };
+
+    auto new_wide = [&]() {
+        out.emplace_back();
+        WideNode& w = out.back();
+        std::memset(&w, 0, sizeof w);
+        for (int c = 0; c < 4; c++) {
+            w.child[c] = kEmptyChild;
+            // an empty slot's box can never pass the slab test (and is skipped by the sentinel anyway)
+            w.lox[c] = w.loy[c] = w.loz[c] = FLT_MAX;
+            w.hix[c] = w.hiy[c] = w.hiz[c] = -FLT_MAX;
+        }
+        return (uint32_t)out.size() - 1;
+    };
+
+    uint32_t root = new_wide();
+    todo.push_back({0, root, 1});
+    while (!todo.empty()) {
+        Item it = todo.back();
+        todo.pop_back();
+        st.depth = std::max(st.depth, it.depth);
+        std::vector<Slot> slots;
+        const RefNode& top = nodes[it.bin];
+        auto push_leaf_chunks = [&](uint32_t bin) {
+            const RefNode& lf = nodes[bin];
+            uint32_t first = (uint32_t)lf.offset, cnt = (uint32_t)(uint16_t)lf.nTris;
+            for (uint32_t o = 0; o < cnt; o += kMaxLeafTris) slots.push_back({bin, first + o, std::min(kMaxLeafTris, cnt - o), true});
+        };
+        if (top.nTris > 0) {
+            push_leaf_chunks(it.bin);
+        } else {
+            slots.push_back({it.bin + 1, 0, 0, false});
+            slots.push_back({(uint32_t)top.offset, 0, 0, false});
+        }
+        // Greedy collapse: keep opening the interior slot with the largest surface area while there is room.
+        while (slots.size() < 4) {
+            int best = -1;
+            float bestA = -1.f;
+            for (size_t k = 0; k < slots.size(); k++) {
+                if (slots[k].chunk || nodes[slots[k].bin].nTris > 0) continue;
+                float a = half_area(nodes[slots[k].bin]);
+                if (!(a <= bestA)) { bestA = a; best = (int)k; }
+            }
+            if (best < 0) break;
+            uint32_t b = slots[best].bin;
+            slots[best] = {b + 1, 0, 0, false};
+            slots.push_back({(uint32_t)nodes[b].offset, 0, 0, false});
+        }
+        // Oversized leaves (> kMaxLeafTris, only via the cmpMax==cmpMin path of bvh.cpp:155-163) may
+        // leave more than 4 slots: spill the tail into a chained wide node with the same boxes.
+        uint32_t cur = it.wide;
+        size_t k = 0;
+        while (k < slots.size()) {
+            size_t room = (slots.size() - k > 4) ? 3 : 4;
+            for (size_t c = 0; c < room && k < slots.size(); c++, k++) {
+                const Slot& s = slots[k];
+                const RefNode& bn = nodes[s.bin];
+                WideNode& w = out[cur];
+                w.lox[c] = bn.mn.x; w.loy[c] = bn.mn.y; w.loz[c] = bn.mn.z;
+                w.hix[c] = bn.mx.x; w.hiy[c] = bn.mx.y; w.hiz[c] = bn.mx.z;
+                if (s.chunk) {
+                    w.child[c] = leaf_ref(s.first, s.count);
+                    st.n_leaf_refs++;
+                } else if (bn.nTris > 0 && (uint32_t)(uint16_t)bn.nTris <= kMaxLeafTris) {
+                    w.child[c] = leaf_ref((uint32_t)bn.offset, (uint32_t)bn.nTris);
+                    st.n_leaf_refs++;
+                } else {
+                    uint32_t child = new_wide();
+                    out[cur].child[c] = (int32_t)child;
+                    todo.push_back({s.bin, child, it.depth + 1});
+                }
+            }
+            if (k < slots.size()) {          // chain: 4th slot points at a continuation node holding the rest
+                const RefNode& bn = nodes[it.bin];
+                uint32_t cont = new_wide();
+                WideNode& w = out[cur];
+                w.lox[3] = bn.mn.x; w.loy[3] = bn.mn.y; w.loz[3] = bn.mn.z;
+                w.hix[3] = bn.mx.x; w.hiy[3] = bn.mx.y; w.hiz[3] = bn.mx.z;
+                w.child[3] = (int32_t)cont;
+                cur = cont;
+            }
+        }
+    }
+    st.n_wide = (uint32_t)out.size();
+    return st;
+}
+
+void make_tri_records(const RefTriangle* tris, uint32_t n, const RefNode* nodes, uint32_t n_nodes,
+                      std::vector<TriIsect>& isect, std::vector<TriShade>& shade) {
+    isect.assign(n, TriIsect{});
+    shade.assign(n, TriShade{});
+    for (uint32_t i = 0; i < n; i++) {
+        const RefTriangle& t = tris[i];
+        TriIsect& a = isect[i];
+        a.v1[0] = t.v1.x; a.v1[1] = t.v1.y; a.v1[2] = t.v1.z;
+        a.e1[0] = t.e1.x; a.e1[1] = t.e1.y; a.e1[2] = t.e1.z;
+        a.e2[0] = t.e2.x; a.e2[1] = t.e2.y; a.e2[2] = t.e2.z;
+        a.materialId = t.materialId;
+        a.leafFirst = 0;
+        TriShade& s = shade[i];
+        std::memset(&s, 0, sizeof s);
+        s.n1[0] = t.n1.x; s.n1[1] = t.n1.y; s.n1[2] = t.n1.z;
+        s.n2[0] = t.n2.x; s.n2[1] = t.n2.y; s.n2[2] = t.n2.z;
+        s.n3[0] = t.n3.x; s.n3[1] = t.n3.y; s.n3[2] = t.n3.z;
+        s.uv1[0] = t.uv1.x; s.uv1[1] = t.uv1.y;
+        s.uv2[0] = t.uv2.x; s.uv2[1] = t.uv2.y;
+        s.uv3[0] = t.uv3.x; s.uv3[1] = t.uv3.y;
+        s.area = t.area;
+        s.materialId = t.materialId;
+    }
+    // The tie rule needs, per triangle, the firstTriOffset of the REFERENCE leaf holding it.
+    for (uint32_t k = 0; k < n_nodes; k++) {
+        if (nodes[k].nTris <= 0) continue;
+        uint32_t first = (uint32_t)nodes[k].offset, cnt = (uint32_t)(uint16_t)nodes[k].nTris;
+        for (uint32_t i = 0; i < cnt && first + i < n; i++) isect[first + i].leafFirst = first;
+    }
+}
+
+}  // namespace crt

@@ -1,0 +1,84 @@
+// cudart_b200/csrc/host_scene.h - host-side scene preparation for the B200 path tracer.
+//
+//  * RefTriangle / RefNode / RefCamera: the reference's POD layouts (geometry.h:30-51, bvh.h:18-27,
+//    camera.h:9-22), the currency of the C ABI.
+//  * build_reference_bvh(): the reference's BVH (bvh.cpp:65-323) rebuilt bit for bit.
+//  * flatten_wide(): that binary tree re-flattened into the 128-byte 4-ary node the kernels read.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace crt {
+
+struct F3 { float x, y, z; };
+struct F2 { float x, y; };
+
+struct RefTriangle {          // 128 B, __attribute__((aligned(128))) in the reference
+    uint32_t triId, materialId;
+    F3 v1, e1, e2, n1, n2, n3;
+    F2 uv1, uv2, uv3;
+    float area;
+    uint8_t pad[20];
+};
+static_assert(sizeof(RefTriangle) == 128, "reference Triangle layout");
+
+struct RefNode {              // 32 B LinearBVHNode
+    F3 mn, mx;
+    int32_t offset;           // leaf: first triangle; interior: index of the second child
+    int16_t nTris, axis;
+};
+static_assert(sizeof(RefNode) == 32, "reference LinearBVHNode layout");
+
+struct RefCamera {            // 72 B
+    F3 eye, dir, up, right;
+    float fov, aspect, apertureWidth, focusDistance;
+    int32_t xpixels, ypixels;
+};
+static_assert(sizeof(RefCamera) == 72, "reference Camera layout");
+
+// ---- device-facing layouts -------------------------------------------------------------------
+// 4-ary node, 128 B = one L1/L2 line, read as eight 16-byte vectors.  Child boxes are the EXACT fp32
+// boxes of the reference's binary nodes (the bit-exact leaf test needs them unrounded), stored SoA so
+// one float4 holds the same plane of all four children.
+struct WideNode {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    int32_t child[4];         // >= 0: index of a WideNode; < 0: leaf, see leaf_ref(); kEmptyChild: unused slot
+    uint32_t aux[4];          // reserved (0)
+};
+static_assert(sizeof(WideNode) == 128, "wide node is one 128-byte line");
+
+constexpr int32_t kEmptyChild = 0x7fffffff;
+constexpr uint32_t kMaxLeafTris = 32;           // per leaf reference; bigger reference leaves are chunked
+constexpr uint32_t kMaxTris = 1u << 26;
+// leaf reference: bit31 set | (count-1) << 26 | first triangle
+inline int32_t leaf_ref(uint32_t first, uint32_t count) { return (int32_t)(0x80000000u | ((count - 1) << 26) | first); }
+
+// Intersection record, 48 B = 3 x float4: (v1, leafFirst bits) (e1, materialId bits) (e2, 0)
+struct TriIsect { float v1[3]; uint32_t leafFirst; float e1[3]; uint32_t materialId; float e2[3]; uint32_t pad; };
+static_assert(sizeof(TriIsect) == 48, "intersection record");
+// Shading record, 80 B = 5 x float4: (n1, area) (n2, materialId bits) (n3, 0) (uv1, uv2) (uv3, 0, 0)
+struct TriShade {
+    float n1[3]; float area;
+    float n2[3]; uint32_t materialId;
+    float n3[3]; uint32_t pad0;
+    float uv1[2], uv2[2];
+    float uv3[2]; uint32_t pad1[2];
+};
+static_assert(sizeof(TriShade) == 80, "shading record");
+
+// Reference BVH, rebuilt.  tris is reordered in place into BVH order.  positions: 9 floats per
+// triangle (the three OBJ vertex positions; the reference boxes them, not v1/e1/e2: bvh.cpp:79-96).
+void build_reference_bvh(RefTriangle* tris, const float* positions, uint32_t n, std::vector<RefNode>& nodes_out);
+
+// Scene::constructLightList.
+void build_light_list(RefTriangle* tris, uint32_t n, float* mat_floats, const int32_t* mat_indices, uint32_t n_mats,
+                      std::vector<uint32_t>& lights, float& lights_area);
+
+struct WideStats { uint32_t n_wide = 0, depth = 0, n_leaf_refs = 0; };
+// Collapse the reference's binary tree into WideNodes (root = 0).
+WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, std::vector<WideNode>& out);
+
+void make_tri_records(const RefTriangle* tris, uint32_t n, const RefNode* nodes, uint32_t n_nodes,
+                      std::vector<TriIsect>& isect, std::vector<TriShade>& shade);
+
+}  // namespace crt

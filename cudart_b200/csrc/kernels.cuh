@@ -1,0 +1,83 @@
+// cudart_b200/csrc/kernels.cuh - device-side data model and kernel launchers of the wavefront path tracer.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "host_scene.h"
+
+namespace crt {
+
+// Read-only scene, resident in HBM (L2/L1 for the bundled scenes).
+struct DScene {
+    const float4* wide;        // n_wide x 8 float4  (WideNode)
+    const float4* tri_isect;   // n_tris x 3 float4  (TriIsect)
+    const float4* tri_shade;   // n_tris x 5 float4  (TriShade)
+    const float4* mats;        // n_mats x 4 float4: (kd, bsdf) (ka, texKdIdx) (ks, 0) (ns, ni, diffuseCoefficient, 0)
+    const uint32_t* lights;
+    const float* tex_data;     // float3 texels
+    const uint32_t* tex_dims;
+    const uint32_t* tex_offsets;
+    uint32_t n_wide, n_tris, n_mats, n_lights, n_tex, tex_texels;
+    float lights_area;
+    float cull_far_rel;        // distance culling margins (ignored with CRT_FLAG_EXACT_VISIT)
+    float cull_far_abs;
+    float cull_behind;
+    RefCamera cam;
+};
+
+// Which pixels this context owns: interleaved row tiles (tile k -> rank k % world).
+struct DTiling {
+    uint32_t W, H, rank, world, tile_rows;
+    uint32_t local_rows;       // rows owned (valid ones; they are a prefix of the padded local rows)
+    uint32_t local_pixels;     // local_rows * W
+    uint32_t padded_pixels;    // identical on all ranks: ceil(n_tiles / world) * tile_rows * W
+};
+
+constexpr int kMaxBounces = 6;                 // renderer.cu:25,33
+
+// Per-wave counters (device memory, zeroed once per wave).
+struct DCounters {
+    uint32_t qcount[kMaxBounces + 1];          // extend queue sizes per bounce
+    uint32_t scount[kMaxBounces];              // shadow queue sizes per bounce
+    uint32_t ehead[kMaxBounces];               // persistent-fetch heads
+    uint32_t shead[kMaxBounces];
+};
+struct DStats {                                // running totals (never reset by a wave)
+    unsigned long long extend_rays, shadow_rays, node_visits, tri_tests, samples;
+};
+
+// Wavefront state for up to `capacity` paths in flight.  Everything is SoA at 16-byte granularity:
+// consecutive lanes touch consecutive float4s.
+struct DWave {
+    float4* rq_o[2];           // extend queue (ping-pong): origin.xyz, tMin
+    float4* rq_d[2];           //                           dir.xyz,    tMax
+    uint32_t* rq_path[2];      //                           path id
+    float4* hits;              // t, u, v, tri (bits) per extend-queue slot
+    float4* sq_o;              // shadow queue: origin.xyz, tMin
+    float4* sq_d;              //               dir.xyz, tMax
+    float4* sq_c;              //               mask*lightColor.rgb, light triangle index (bits)
+    uint32_t* sq_path;
+    float4* st_mask;           // per path: throughput.rgb, meta bits (dim | bounce<<8 | prevBsdf<<12)
+    uint32_t* st_key;          // per path: RNG key
+    float4* color;             // per path: radiance accumulated so far
+    DCounters* counters;
+    DStats* stats;
+    uint32_t capacity;
+};
+
+struct LaunchCfg { int sms; cudaStream_t stream; };
+
+void launch_raygen(const DScene& sc, const DTiling& tl, const DWave& wv, uint32_t first_sample, uint32_t wave_spp,
+                   uint32_t seed, const LaunchCfg& cfg);
+void launch_extend(const DScene& sc, const DWave& wv, int bounce, bool exact, bool stats, const LaunchCfg& cfg);
+void launch_shade(const DScene& sc, const DTiling& tl, const DWave& wv, int bounce, const LaunchCfg& cfg);
+void launch_shadow(const DScene& sc, const DWave& wv, int bounce, bool exact, bool stats, const LaunchCfg& cfg);
+void launch_accumulate(const DTiling& tl, const DWave& wv, float4* accum, uint32_t wave_spp, const LaunchCfg& cfg);
+// Stand-alone closest-hit over a flat ray array (crt_trace_closest): rays as 8 floats, hits as (t,u,v,tri).
+void launch_trace(const DScene& sc, const float4* rays, uint32_t n, float4* hits, uint32_t* head, DStats* stats,
+                  bool exact, bool with_stats, const LaunchCfg& cfg);
+// Resolve: accum is rank-major (world x padded_pixels float4) when gathered, else this rank's compact buffer.
+void launch_resolve(const DTiling& tl, const float4* accum, bool gathered, uint32_t spp, const uint8_t* gamma_lut,
+                    uchar4* rgba_out, float* f32_out, int f32_mode /*0 none,1 mean,2 sum*/, const LaunchCfg& cfg);
+
+}  // namespace crt

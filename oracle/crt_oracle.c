@@ -189,7 +189,11 @@ static int intersectBVH(const Node* bvh, const Tri* tris, SurfaceInteraction* si
 int orc_trace_closest(const orc_scene* s, const orc_ray* rays, size_t n, orc_hit* hits, orc_counters* c) {
     const Node* bvh = (const Node*)s->nodes;
     const Tri* tris = (const Tri*)s->tris;
-    for (size_t i = 0; i < n; i++) {
+    /* counters are a single-thread affair; without them the rays are independent */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 4096) if (c == NULL && n > 65536)
+#endif
+    for (int64_t i = 0; i < (int64_t)n; i++) {
         Ray ray;
         memcpy(&ray, &rays[i], sizeof ray);
         SurfaceInteraction si;

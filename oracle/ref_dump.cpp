@@ -52,7 +52,7 @@ int main(int argc, char** argv) {
     const char* tex = arg(argc, argv, "--textures");
     if (!obj || !cam || !tex) {
         fprintf(stderr, "usage: ref_dump --obj X.obj --camera X-camera.json --textures DIR/ -w W -h H\n"
-                        "  [--scene-out F] [--pretris-out F] [--rays-in F --hits-out F]\n"
+                        "  [--scene-out F] [--pretris-out F] [--positions-out F] [--premats-out F] [--rays-in F --hits-out F]\n"
                         "  [--spp S --seed K --accum-out F] [--rgba-out F]\n");
         return 1;
     }
@@ -79,8 +79,28 @@ int main(int argc, char** argv) {
         fclose(f);
     }
 
+    if (const char* p = arg(argc, argv, "--premats-out")) {
+        // material floats BEFORE constructLightList scales ka by the total light area (scene.cpp:161-164)
+        Material* m0 = scene.getMaterialsPtr();
+        FILE* f = fopen(p, "wb");
+        for (uint32_t i = 0; i < scene.getNumMaterials(); i++) {
+            float3 aux = make_float3(m0[i].ns, m0[i].ni, m0[i].diffuseCoefficient);
+            put(f, &m0[i].kd, 12); put(f, &m0[i].ka, 12); put(f, &m0[i].ks, 12); put(f, &aux, 12);
+        }
+        fclose(f);
+    }
+
     auto tb0 = std::chrono::high_resolution_clock::now();
     scene.constructBvh();
+    if (const char* p = arg(argc, argv, "--positions-out")) {
+        // the three vertex positions per triangle that createTriangleBboxes boxes (bvh.cpp:79-96), OBJ order
+        objl::Vertex* vtx = scene.getVertexPtr();
+        uint* idx = scene.getVertexIndicesPtr();
+        FILE* f = fopen(p, "wb");
+        for (uint32_t i = 0; i < nTris; i++)
+            for (int k = 0; k < 3; k++) put(f, &vtx[idx[3 * i + k]].Position, 12);
+        fclose(f);
+    }
     auto tb1 = std::chrono::high_resolution_clock::now();
     scene.constructLightList();
     fprintf(stderr, "ref_dump: bvh build %.3f s\n", std::chrono::duration<double>(tb1 - tb0).count());

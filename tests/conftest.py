@@ -31,6 +31,7 @@ def golden():
                 "pretris": z["pretris"].view(TRIANGLE_DTYPE),
                 "rays": z["rays"].view(RAY_DTYPE),
                 "hits": z["hits"].view(HIT_DTYPE),
+                "positions": z["positions"], "premats": z["premats"],
                 "accum": z["accum"],
                 "rgba": z["rgba"],
                 "W": int(z["meta"][0]), "H": int(z["meta"][1]), "spp": int(z["meta"][2]), "seed": int(z["meta"][3]),

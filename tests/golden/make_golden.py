@@ -113,7 +113,8 @@ def main():
     for scene, W, H, spp in SCENES:
         with tempfile.TemporaryDirectory() as tmp:
             crts, pre = f"{tmp}/s.crts", f"{tmp}/pre.bin"
-            ref_dump(scene, W, H, "--scene-out", crts, "--pretris-out", pre)
+            ref_dump(scene, W, H, "--scene-out", crts, "--pretris-out", pre, "--positions-out", f"{tmp}/pos.bin",
+                     "--premats-out", f"{tmp}/premats.bin")
             fs = load_crts(crts)
             rays = make_rays(fs, rng)
             rays.tofile(f"{tmp}/rays.bin")
@@ -123,10 +124,12 @@ def main():
             accum = np.fromfile(f"{tmp}/accum.bin", np.float32).reshape(H, W, 3)
             rgba = np.fromfile(f"{tmp}/rgba.bin", np.uint8).reshape(H, W, 4)
             pretris = np.fromfile(pre, TRIANGLE_DTYPE)
+            positions = np.fromfile(f"{tmp}/pos.bin", np.float32).reshape(-1, 9)
+            premats = np.fromfile(f"{tmp}/premats.bin", np.float32).reshape(-1, 4, 3)
             with open(crts, "rb") as fi, gzip.GzipFile(f"{OUT}/{scene}.crts.gz", "wb", compresslevel=9, mtime=0) as fo:
                 shutil.copyfileobj(fi, fo)
             np.savez_compressed(f"{OUT}/{scene}.golden.npz", pretris=pretris.view(np.uint8), rays=rays.view(np.uint8),
-                                hits=hits.view(np.uint8), accum=accum, rgba=rgba,
+                                hits=hits.view(np.uint8), accum=accum, rgba=rgba, positions=positions, premats=premats,
                                 meta=np.array([W, H, spp, 1], np.int64))
             nh = int((hits["tri"] != 0xFFFFFFFF).sum())
             print(f"{scene}: {fs.n_tris} tris, {fs.n_nodes} nodes, {len(rays)} rays ({nh} hit), {W}x{H}x{spp}spp")

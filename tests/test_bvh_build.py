@@ -1,0 +1,66 @@
+"""The product's host scene build (csrc/host_scene.cpp through the C ABI) against the reference's own dump:
+same tree node for node, same triangle permutation, same light list / ka scaling.  CPU only - these entry
+points need no GPU."""
+import numpy as np
+import pytest
+
+from conftest import SCENES
+from cudart_b200 import scenebuild
+from cudart_b200.scenefile import EMISSIVE
+
+
+def same_triangles(a, b, skip=()):
+    """Field-wise bit equality (the 20 tail bytes of the reference's 128-byte Triangle are uninitialised padding)."""
+    return all(np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)) for k in a.dtype.names if k not in skip)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_bvh_equals_reference_tree(golden, name):
+    fs, g = golden(name)
+    tris, nodes = scenebuild.build_bvh(g["pretris"], g["positions"])
+    assert nodes.shape[0] == fs.n_nodes
+    # bounds with == so that -0 == +0 (sign of zero differs between -O0 and -O2 builds)
+    assert np.array_equal(nodes["min"], fs.nodes["min"]) and np.array_equal(nodes["max"], fs.nodes["max"])
+    for k in ("offset", "numTriangles", "axis"):
+        assert np.array_equal(nodes[k], fs.nodes[k]), k
+    # triangle permutation: everything but _triId (which constructLightList rewrites for lights)
+    assert same_triangles(tris, fs.tris, skip=("triId",))
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_light_list_and_emission_scaling(golden, name):
+    fs, g = golden(name)
+    tris, _ = scenebuild.build_bvh(g["pretris"], g["positions"])
+    tris, mf, lights, area = scenebuild.build_lights(tris, g["premats"], fs.mat_indices)
+    assert np.array_equal(lights, fs.light_indices)
+    assert np.float32(area) == np.float32(fs.lights_area)
+    assert np.array_equal(mf.reshape(-1, 4, 3).view(np.uint32), fs.mat_floats.view(np.uint32))
+    assert same_triangles(tris, fs.tris)
+    assert all(fs.mat_indices[fs.tris["materialId"][i], 0] == EMISSIVE for i in lights)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_wide_flattening_covers_every_reference_leaf_once(golden, name):
+    fs, _ = golden(name)
+    wide = scenebuild.wide_bvh(fs.nodes)
+    child = wide[:, 24:28].view(np.int32)
+    lo = wide[:, 0:12].view(np.float32).reshape(-1, 3, 4)
+    hi = wide[:, 12:24].view(np.float32).reshape(-1, 3, 4)
+    leaves = fs.nodes[fs.nodes["numTriangles"] > 0]
+    want = {(int(l["offset"]), int(l["numTriangles"])): (l["min"], l["max"]) for l in leaves}
+    seen, interior = {}, []
+    for n in range(wide.shape[0]):
+        for c in range(4):
+            ref = int(child[n, c])
+            if ref == 0x7FFFFFFF:
+                continue
+            if ref < 0:
+                first, cnt = ref & 0x03FFFFFF, ((ref >> 26) & 31) + 1
+                assert (first, cnt) not in seen
+                seen[(first, cnt)] = (lo[n, :, c], hi[n, :, c])
+            else:
+                interior.append(ref)
+    assert set(seen) == set(want)                       # fixture leaves all hold <= 32 triangles
+    for k, (mn, mx) in seen.items():                    # leaf boxes are the reference's, bit for bit
+        assert np.array_equal(mn, want[k][0]) and np.array_equal(mx, want[k][1])
+    assert sorted(interior) == list(range(1, wide.shape[0]))   # every wide node but the root has one parent
