@@ -230,6 +230,12 @@ int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_option
         sc.cull_far_rel = 1.02f;
         sc.cull_far_abs = 1e-3f * diag;
         sc.cull_behind = -2e-2f * diag;
+        bool bounded = true;
+        for (uint32_t k = 0; k < s->n_nodes && bounded; k++) {
+            const float v[6] = {nodes[k].mn.x, nodes[k].mn.y, nodes[k].mn.z, nodes[k].mx.x, nodes[k].mx.y, nodes[k].mx.z};
+            for (float f : v) bounded = bounded && std::isfinite(f) && std::fabs(f) < 1e8f;
+        }
+        sc.coords_bounded = bounded ? 1 : 0;
     }
 
     // ---- pixel ownership ----

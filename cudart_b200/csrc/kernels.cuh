@@ -22,6 +22,7 @@ struct DScene {
     float cull_far_rel;        // distance culling margins (ignored with CRT_FLAG_EXACT_VISIT)
     float cull_far_abs;
     float cull_behind;
+    int coords_bounded;        // every node/triangle coordinate is finite and below 1e8 in magnitude
     RefCamera cam;
 };
 

@@ -34,6 +34,7 @@ def golden():
                 "positions": z["positions"], "premats": z["premats"],
                 "accum": z["accum"],
                 "rgba": z["rgba"],
+                "accum_hi": z["accum_hi"], "hi": tuple(int(v) for v in z["meta"][4:7]),
                 "W": int(z["meta"][0]), "H": int(z["meta"][1]), "spp": int(z["meta"][2]), "seed": int(z["meta"][3]),
             }
             cache[name] = (fs, g)

@@ -16,6 +16,7 @@ oracle/ref_dump.cpp) and stores under tests/golden/:
                        rays/hits: a seeded ray set and the records of the reference's intersectBVH
                        accum    : float radiance sums of the reference's samplePixel, srand(1)
                        rgba     : bytes through the reference's Renderer API (float3ToUchar4 + gamma)
+                       accum_hi : the same sums for a 32x24 image at 256 spp (statistical parity test)
                        meta     : W, H, spp, seed
 
 The ray set mixes (a) rays harvested from the path loop (camera, bounce and shadow rays),
@@ -44,6 +45,7 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 #        scene          W   H  spp
 SCENES = [("cornell", 64, 48, 4), ("cornellSphere", 64, 48, 4), ("monkeys", 64, 48, 4), ("terrain64", 48, 32, 2)]
 N_HARVEST, N_RANDOM, N_SPECIAL = 6000, 3000, 3000
+HI_W, HI_H, HI_SPP = 32, 24, 256
 
 
 def ref_dump(scene, W, H, *extra):
@@ -120,6 +122,9 @@ def main():
             rays.tofile(f"{tmp}/rays.bin")
             ref_dump(scene, W, H, "--rays-in", f"{tmp}/rays.bin", "--hits-out", f"{tmp}/hits.bin", "--spp", str(spp),
                      "--seed", "1", "--accum-out", f"{tmp}/accum.bin", "--rgba-out", f"{tmp}/rgba.bin")
+            # a small, well-sampled image from the reference's samplePixel for the statistical parity test
+            ref_dump(scene, HI_W, HI_H, "--spp", str(HI_SPP), "--seed", "1", "--accum-out", f"{tmp}/accum_hi.bin")
+            accum_hi = np.fromfile(f"{tmp}/accum_hi.bin", np.float32).reshape(HI_H, HI_W, 3)
             hits = np.fromfile(f"{tmp}/hits.bin", HIT_DTYPE)
             accum = np.fromfile(f"{tmp}/accum.bin", np.float32).reshape(H, W, 3)
             rgba = np.fromfile(f"{tmp}/rgba.bin", np.uint8).reshape(H, W, 4)
@@ -130,7 +135,7 @@ def main():
                 shutil.copyfileobj(fi, fo)
             np.savez_compressed(f"{OUT}/{scene}.golden.npz", pretris=pretris.view(np.uint8), rays=rays.view(np.uint8),
                                 hits=hits.view(np.uint8), accum=accum, rgba=rgba, positions=positions, premats=premats,
-                                meta=np.array([W, H, spp, 1], np.int64))
+                                accum_hi=accum_hi, meta=np.array([W, H, spp, 1, HI_W, HI_H, HI_SPP], np.int64))
             nh = int((hits["tri"] != 0xFFFFFFFF).sum())
             print(f"{scene}: {fs.n_tris} tris, {fs.n_nodes} nodes, {len(rays)} rays ({nh} hit), {W}x{H}x{spp}spp")
 
