@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libcrt_b200.so")
 CRT_FLAG_EXACT_VISIT = 1
 CRT_FLAG_PROFILE = 2
 CRT_FLAG_STATS = 4
+CRT_FLAG_REFERENCE_TOPOLOGY = 8
 CRT_MISS = 0xFFFFFFFF
 STAGES = ("raygen", "extend", "shade", "shadow", "accumulate")
 

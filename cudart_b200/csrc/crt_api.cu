@@ -68,7 +68,7 @@ struct crt_ctx {
     DWave wv{};
     WideStats wide_stats{};
     // scene
-    DevBuf<float4> wide, tri_isect, tri_shade, mats;
+    DevBuf<float4> wide, tri_isect, tri_shade, mats, light_boxes;
     DevBuf<uint32_t> lights, tex_dims, tex_offsets;
     DevBuf<float> tex_data;
     // wave
@@ -99,7 +99,7 @@ int upload(DevBuf<T>& b, const void* src, size_t count, cudaStream_t s) {
 void free_all(crt_ctx* c) {
     cudaSetDevice(c->device);
     c->wide.release(); c->tri_isect.release(); c->tri_shade.release(); c->mats.release();
-    c->lights.release(); c->tex_dims.release(); c->tex_offsets.release(); c->tex_data.release();
+    c->lights.release(); c->light_boxes.release(); c->tex_dims.release(); c->tex_offsets.release(); c->tex_data.release();
     for (int i = 0; i < 2; i++) { c->rq_o[i].release(); c->rq_d[i].release(); c->rq_path[i].release(); }
     c->hits.release(); c->sq_o.release(); c->sq_d.release(); c->sq_c.release(); c->st_mask.release(); c->color.release();
     c->sq_path.release(); c->st_key.release(); c->counters.release(); c->stats.release(); c->accum.release();
@@ -178,7 +178,12 @@ int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_option
     for (uint32_t k = 0; k < s->n_lights; k++)
         if (s->light_indices[k] >= s->n_tris) return bail(fail(CRT_ERR_INVALID, "crt_create: light index out of range"));
     std::vector<WideNode> wide;
-    c->wide_stats = flatten_wide(nodes, s->n_nodes, wide);
+    {
+        std::vector<RefNode> clustered;
+        if (!(o.flags & CRT_FLAG_REFERENCE_TOPOLOGY)) recluster_leaves(nodes, s->n_nodes, clustered);
+        c->wide_stats = clustered.empty() ? flatten_wide(nodes, s->n_nodes, tris, s->n_tris, wide)
+                                          : flatten_wide(clustered.data(), (uint32_t)clustered.size(), tris, s->n_tris, wide);
+    }
     if (3 * c->wide_stats.depth + 4 > 64) return bail(fail(CRT_ERR_LIMIT, "crt_create: wide BVH depth %u exceeds the traversal stack", c->wide_stats.depth));
     std::vector<TriIsect> isect;
     std::vector<TriShade> shade;
@@ -204,6 +209,19 @@ int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_option
     UP(tri_shade, shade.data(), shade.size() * 5);
     UP(mats, mats.data(), mats.size());
     UP(lights, s->light_indices, s->n_lights);
+    std::vector<float4> lboxes(2 * (size_t)s->n_lights);
+    {   // the reference leaf holding each light triangle
+        std::vector<uint32_t> leaf_of_first(s->n_tris, 0xffffffffu);
+        for (uint32_t j = 0; j < s->n_nodes; j++)
+            if (nodes[j].nTris > 0) leaf_of_first[(uint32_t)nodes[j].offset] = j;
+        for (uint32_t k = 0; k < s->n_lights; k++) {
+            const uint32_t j = leaf_of_first[isect[s->light_indices[k]].leafFirst];
+            if (j == 0xffffffffu) return bail(fail(CRT_ERR_INVALID, "crt_create: light %u is in no BVH leaf", k));
+            lboxes[2 * k] = make_float4(nodes[j].mn.x, nodes[j].mn.y, nodes[j].mn.z, 0.f);
+            lboxes[2 * k + 1] = make_float4(nodes[j].mx.x, nodes[j].mx.y, nodes[j].mx.z, 0.f);
+        }
+    }
+    UP(light_boxes, lboxes.data(), lboxes.size());
     UP(tex_dims, s->tex_dims, 2 * (size_t)s->n_tex);
     UP(tex_offsets, s->tex_offsets, s->n_tex ? s->n_tex + 1 : 0);
     UP(tex_data, s->tex_data, 3 * (size_t)s->tex_texels);
@@ -216,20 +234,13 @@ int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_option
 #undef UP
     DScene& sc = c->sc;
     sc.wide = c->wide.p; sc.tri_isect = c->tri_isect.p; sc.tri_shade = c->tri_shade.p; sc.mats = c->mats.p;
-    sc.lights = c->lights.p; sc.tex_data = c->tex_data.p; sc.tex_dims = c->tex_dims.p; sc.tex_offsets = c->tex_offsets.p;
+    sc.lights = c->lights.p; sc.light_boxes = c->light_boxes.p; sc.tex_data = c->tex_data.p; sc.tex_dims = c->tex_dims.p; sc.tex_offsets = c->tex_offsets.p;
     sc.n_wide = (uint32_t)wide.size(); sc.n_tris = s->n_tris; sc.n_mats = s->n_mats; sc.n_lights = s->n_lights;
     sc.n_tex = s->n_tex; sc.tex_texels = s->tex_texels; sc.lights_area = s->lights_area;
     memcpy(&sc.cam, s->camera, sizeof(RefCamera));
     sc.cam.xpixels = (int32_t)W;
     sc.cam.ypixels = (int32_t)H;
-    {   // culling margins, relative to the scene's extent (DESIGN.md "distance culling")
-        const RefNode& r = nodes[0];
-        float dx = r.mx.x - r.mn.x, dy = r.mx.y - r.mn.y, dz = r.mx.z - r.mn.z;
-        float diag = sqrtf(dx * dx + dy * dy + dz * dz);
-        if (!(diag > 0.f) || !std::isfinite(diag)) diag = 1.f;
-        sc.cull_far_rel = 1.02f;
-        sc.cull_far_abs = 1e-3f * diag;
-        sc.cull_behind = -2e-2f * diag;
+    {
         bool bounded = true;
         for (uint32_t k = 0; k < s->n_nodes && bounded; k++) {
             const float v[6] = {nodes[k].mn.x, nodes[k].mn.y, nodes[k].mn.z, nodes[k].mx.x, nodes[k].mx.y, nodes[k].mx.z};
@@ -489,7 +500,9 @@ int crt_build_lights(void* tris, uint32_t n_tris, float* mat_floats, const int32
 int crt_wide_bvh(const void* nodes, uint32_t n_nodes, void* wide_out, uint32_t cap, uint32_t* n_wide_out) {
     if (!nodes || !n_wide_out) return fail(CRT_ERR_INVALID, "crt_wide_bvh: null argument");
     std::vector<WideNode> wide;
-    flatten_wide((const RefNode*)nodes, n_nodes, wide);
+    std::vector<RefNode> clustered;
+    recluster_leaves((const RefNode*)nodes, n_nodes, clustered);
+    flatten_wide(clustered.data(), (uint32_t)clustered.size(), nullptr, 0, wide);
     *n_wide_out = (uint32_t)wide.size();
     if (wide_out) memcpy(wide_out, wide.data(), std::min<size_t>(cap, wide.size()) * sizeof(WideNode));
     return CRT_OK;

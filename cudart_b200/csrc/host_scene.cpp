@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cstring>
 
 namespace crt {
@@ -222,10 +223,149 @@ inline float half_area(const RefNode& n) {
 }
 }  // namespace
 
-WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, std::vector<WideNode>& out) {
+// ---- SAH re-clustering of the reference's leaves ----------------------------------------------------
+// Which triangles a ray tests is decided by the reference's LEAF boxes alone; the interior
+// structure above them only has to be conservative.  The reference builder's interior structure is poor (its
+// "surface area" is a volume, its centroid bounds always include the origin: ~100 node visits per ray on
+// monkeys), so the leaves are re-clustered here with a conventional binned surface-area heuristic.  The result
+// is emitted in the reference's own pre-order LinearBVHNode format (leaf records copied verbatim, interior boxes
+// = exact min/max unions) and then collapsed to 4-ary nodes like the reference tree would be.
+namespace {
+struct LeafRef { uint32_t node; F3 c; };
+
+struct Recluster {
+    const RefNode* ref;
+    std::vector<LeafRef> leaves;
+    std::vector<RefNode> out;
+
+    static float area(const F3& mn, const F3& mx) {
+        float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z;
+        return dx * dy + dy * dz + dz * dx;
+    }
+    uint32_t build(uint32_t lo, uint32_t hi) {          // [lo, hi) of `leaves`; returns index in `out`
+        const uint32_t my = (uint32_t)out.size();
+        out.emplace_back();
+        if (hi - lo == 1) { out[my] = ref[leaves[lo].node]; return my; }
+        F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}, cmn = mn, cmx = mx;
+        for (uint32_t i = lo; i < hi; i++) {
+            const RefNode& l = ref[leaves[i].node];
+            mn = lo3(mn, l.mn); mx = hi3(mx, l.mx);
+            cmn = lo3(cmn, leaves[i].c); cmx = hi3(cmx, leaves[i].c);
+        }
+        constexpr int kBins = 16;
+        int bestAxis = -1, bestSplit = 0;
+        float bestCost = FLT_MAX;
+        for (int ax = 0; ax < 3; ax++) {
+            const float c0 = axis_of(cmn, ax), c1 = axis_of(cmx, ax);
+            if (!(c1 > c0)) continue;
+            struct Bin { F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}; uint32_t w = 0; } bins[kBins];
+            const float scale = kBins / (c1 - c0);
+            for (uint32_t i = lo; i < hi; i++) {
+                int b = (int)((axis_of(leaves[i].c, ax) - c0) * scale);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                const RefNode& l = ref[leaves[i].node];
+                bins[b].mn = lo3(bins[b].mn, l.mn); bins[b].mx = hi3(bins[b].mx, l.mx);
+                bins[b].w += (uint32_t)(uint16_t)l.nTris;
+            }
+            float rightA[kBins]; uint32_t rightW[kBins];
+            F3 rmn{FLT_MAX, FLT_MAX, FLT_MAX}, rmx{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            uint32_t rw = 0;
+            for (int b = kBins - 1; b > 0; b--) {
+                rmn = lo3(rmn, bins[b].mn); rmx = hi3(rmx, bins[b].mx); rw += bins[b].w;
+                rightA[b] = rw ? area(rmn, rmx) : 0.f; rightW[b] = rw;
+            }
+            F3 lmn{FLT_MAX, FLT_MAX, FLT_MAX}, lmx{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            uint32_t lw = 0;
+            for (int b = 0; b < kBins - 1; b++) {
+                lmn = lo3(lmn, bins[b].mn); lmx = hi3(lmx, bins[b].mx); lw += bins[b].w;
+                if (!lw || !rightW[b + 1]) continue;
+                const float cost = area(lmn, lmx) * lw + rightA[b + 1] * rightW[b + 1];
+                if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestSplit = b; }
+            }
+        }
+        uint32_t mid;
+        if (bestAxis >= 0) {
+            const float c0 = axis_of(cmn, bestAxis), scale = kBins / (axis_of(cmx, bestAxis) - c0);
+            LeafRef* m = std::partition(leaves.data() + lo, leaves.data() + hi, [&](const LeafRef& l) {
+                int b = (int)((axis_of(l.c, bestAxis) - c0) * scale);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                return b <= bestSplit;
+            });
+            mid = (uint32_t)(m - leaves.data());
+        } else {
+            mid = lo;
+        }
+        if (mid == lo || mid == hi) mid = (lo + hi) / 2;      // coincident centroids: split by count
+        build(lo, mid);
+        const uint32_t second = build(mid, hi);
+        RefNode& nd = out[my];
+        std::memset(&nd, 0, sizeof nd);
+        nd.mn = mn; nd.mx = mx;
+        nd.offset = (int32_t)second;
+        nd.nTris = 0; nd.axis = 0;
+        return my;
+    }
+};
+}  // namespace
+
+void recluster_leaves(const RefNode* nodes, uint32_t n_nodes, std::vector<RefNode>& out) {
+    Recluster rc;
+    rc.ref = nodes;
+    for (uint32_t k = 0; k < n_nodes; k++)
+        if (nodes[k].nTris > 0)
+            rc.leaves.push_back({k, {(nodes[k].mn.x + nodes[k].mx.x) * 0.5f, (nodes[k].mn.y + nodes[k].mx.y) * 0.5f,
+                                     (nodes[k].mn.z + nodes[k].mx.z) * 0.5f}});
+    out.clear();
+    if (rc.leaves.empty()) return;
+    rc.out.reserve(2 * rc.leaves.size());
+    rc.build(0, (uint32_t)rc.leaves.size());
+    out.swap(rc.out);
+}
+
+CullBound triangle_cull_bound(const RefTriangle& t) {
+    // Forward error of Triangle::intersect's t = (e2 . (T x e1)) / (e1 . (d x e2)) in fp32 (eps = 2^-24), |d| <= 1:
+    //   |dt| <= 5 eps |e1||e2| (|T| + |t|) / |det|,  and the reference only accepts |det| >= 1e-5 (geometry.cu:43),
+    //   |T| <= |t| + L with L the triangle's longest edge.  Hence  t_computed >= t (1 - 2s) - s L,
+    //   s = 5 eps |e1||e2| / 1e-5 ~= 0.03 |e1||e2|; we use 0.06 (2x safety) and give up beyond s = 0.25.
+    auto len = [](const F3& v) { return std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z); };
+    const F3 e3{t.e2.x - t.e1.x, t.e2.y - t.e1.y, t.e2.z - t.e1.z};
+    const float l1 = len(t.e1), l2 = len(t.e2), l3 = len(e3);
+    const float s = 0.06f * l1 * l2, L = std::max(l1, std::max(l2, l3));
+    if (!(s < 0.25f) || !std::isfinite(L)) return {0.f, INFINITY};
+    return {1.f - 2.f * s - 1e-6f, s * L + 1e-6f * L};
+}
+
+uint32_t pack_cull_bound(CullBound b) {
+    uint32_t a, bb;
+    std::memcpy(&a, &b.A, 4);
+    std::memcpy(&bb, &b.B, 4);
+    a &= 0xffff0000u;                                           // A rounded down (positive)
+    if (bb & 0xffffu) bb = (bb + 0x10000u) & 0xffff0000u;       // B rounded up
+    return a | (bb >> 16);
+}
+
+WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, const RefTriangle* tris, uint32_t n_tris, std::vector<WideNode>& out) {
     WideStats st;
     out.clear();
     if (n_nodes == 0) return st;
+    // cull bound per binary node, bottom-up (children always have larger indices in the pre-order layout)
+    std::vector<CullBound> cb(n_nodes);
+    for (uint32_t k = n_nodes; k-- > 0;) {
+        const RefNode& nd = nodes[k];
+        CullBound b{1.f, 0.f};
+        if (nd.nTris > 0) {
+            for (uint32_t i = 0; i < (uint32_t)(uint16_t)nd.nTris && (uint32_t)nd.offset + i < n_tris; i++) {
+                const CullBound t = triangle_cull_bound(tris[(uint32_t)nd.offset + i]);
+                b.A = std::min(b.A, t.A);
+                b.B = std::max(b.B, t.B);
+            }
+        } else {
+            const CullBound &l = cb[k + 1], &r = cb[(uint32_t)nd.offset];
+            b.A = std::min(l.A, r.A);
+            b.B = std::max(l.B, r.B);
+        }
+        cb[k] = b;
+    }
     struct Item { uint32_t bin; uint32_t wide; uint32_t depth; };
     std::vector<Item> todo;
 
@@ -290,6 +430,7 @@ WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, std::vector<WideN
                 WideNode& w = out[cur];
                 w.lox[c] = bn.mn.x; w.loy[c] = bn.mn.y; w.loz[c] = bn.mn.z;
                 w.hix[c] = bn.mx.x; w.hiy[c] = bn.mx.y; w.hiz[c] = bn.mx.z;
+                w.aux[c] = pack_cull_bound(cb[s.bin]);
                 if (s.chunk) {
                     w.child[c] = leaf_ref(s.first, s.count);
                     st.n_leaf_refs++;
@@ -308,6 +449,7 @@ WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, std::vector<WideN
                 WideNode& w = out[cur];
                 w.lox[3] = bn.mn.x; w.loy[3] = bn.mn.y; w.loz[3] = bn.mn.z;
                 w.hix[3] = bn.mx.x; w.hiy[3] = bn.mx.y; w.hiz[3] = bn.mx.z;
+                w.aux[3] = pack_cull_bound(cb[it.bin]);
                 w.child[3] = (int32_t)cont;
                 cur = cont;
             }

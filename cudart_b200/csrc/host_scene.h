@@ -43,7 +43,7 @@ static_assert(sizeof(RefCamera) == 72, "reference Camera layout");
 struct WideNode {
     float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
     int32_t child[4];         // >= 0: index of a WideNode; < 0: leaf, see leaf_ref(); kEmptyChild: unused slot
-    uint32_t aux[4];          // reserved (0)
+    uint32_t aux[4];          // per child: packed CullBound of the subtree (pack_cull_bound)
 };
 static_assert(sizeof(WideNode) == 128, "wide node is one 128-byte line");
 
@@ -74,9 +74,21 @@ void build_reference_bvh(RefTriangle* tris, const float* positions, uint32_t n, 
 void build_light_list(RefTriangle* tris, uint32_t n, float* mat_floats, const int32_t* mat_indices, uint32_t n_mats,
                       std::vector<uint32_t>& lights, float& lights_area);
 
+// Re-cluster the reference's leaves under a binned-SAH interior structure (leaf records and boxes verbatim).
+void recluster_leaves(const RefNode* nodes, uint32_t n_nodes, std::vector<RefNode>& out);
+
 struct WideStats { uint32_t n_wide = 0, depth = 0, n_leaf_refs = 0; };
 // Collapse the reference's binary tree into WideNodes (root = 0).
-WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, std::vector<WideNode>& out);
+WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, const RefTriangle* tris, uint32_t n_tris, std::vector<WideNode>& out);
+
+// Distance-culling bound of a subtree (DESIGN.md "distance culling"): for every triangle below, a Moeller-Trumbore
+// t computed in fp32 by the reference's operation sequence satisfies  t_computed >= t_true * A - B  for rays with
+// |dir| <= 1, so a child whose box entry distance t0 gives t0 * A - B > best cannot hold the closest hit.
+// A = 0, B = +inf marks a subtree that must never be culled (triangles too large for the bound to mean anything).
+struct CullBound { float A, B; };
+CullBound triangle_cull_bound(const RefTriangle& t);
+// aux word of a WideNode child: bf16(A) rounded down in the high half, bf16(B) rounded up in the low half
+uint32_t pack_cull_bound(CullBound b);
 
 void make_tri_records(const RefTriangle* tris, uint32_t n, const RefNode* nodes, uint32_t n_nodes,
                       std::vector<TriIsect>& isect, std::vector<TriShade>& shade);

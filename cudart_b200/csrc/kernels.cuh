@@ -14,14 +14,12 @@ struct DScene {
     const float4* tri_shade;   // n_tris x 5 float4  (TriShade)
     const float4* mats;        // n_mats x 4 float4: (kd, bsdf) (ka, texKdIdx) (ks, 0) (ns, ni, diffuseCoefficient, 0)
     const uint32_t* lights;
+    const float4* light_boxes; // per light: the reference leaf box holding it (lo.xyz, hi.xyz), for the shadow seed
     const float* tex_data;     // float3 texels
     const uint32_t* tex_dims;
     const uint32_t* tex_offsets;
     uint32_t n_wide, n_tris, n_mats, n_lights, n_tex, tex_texels;
     float lights_area;
-    float cull_far_rel;        // distance culling margins (ignored with CRT_FLAG_EXACT_VISIT)
-    float cull_far_abs;
-    float cull_behind;
     int coords_bounded;        // every node/triangle coordinate is finite and below 1e8 in magnitude
     RefCamera cam;
 };
@@ -56,7 +54,7 @@ struct DWave {
     float4* hits;              // t, u, v, tri (bits) per extend-queue slot
     float4* sq_o;              // shadow queue: origin.xyz, tMin
     float4* sq_d;              //               dir.xyz, tMax
-    float4* sq_c;              //               mask*lightColor.rgb, light triangle index (bits)
+    float4* sq_c;              //               mask*lightColor.rgb, light ordinal (bits)
     uint32_t* sq_path;
     float4* st_mask;           // per path: throughput.rgb, meta bits (dim | bounce<<8 | prevBsdf<<12)
     uint32_t* st_key;          // per path: RNG key

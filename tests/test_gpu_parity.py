@@ -56,6 +56,16 @@ def test_closest_hit_bit_exact_on_a_million_path_rays(golden, B200Renderer, name
     r.close()
 
 
+@pytest.mark.parametrize("name", SCENES)
+def test_closest_hit_is_independent_of_interior_topology(golden, B200Renderer, name):
+    """Reference interior structure vs SAH re-clustered leaves: same records, bit for bit, culled or not."""
+    fs, g = golden(name)
+    r = B200Renderer(fs, g["W"], g["H"], reference_topology=True)
+    assert_hits_equal(r.trace_closest(g["rays"], exact_visit=True), g["hits"])
+    assert_hits_equal(r.trace_closest(g["rays"], exact_visit=False), g["hits"])
+    r.close()
+
+
 def test_empty_and_ragged_ray_batches(golden, B200Renderer):
     fs, g = golden("cornellSphere")
     r = B200Renderer(fs, g["W"], g["H"])

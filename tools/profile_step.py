@@ -13,10 +13,11 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "cornellSphere_1080p"
 spp = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 waves = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 scene, W, H, _ = WORKLOADS[wl]
-r = B200Renderer(load_scene(scene, W, H), W, H, spp, spp_per_wave=spp, stats=bool(os.environ.get("CRT_STATS")))
+r = B200Renderer(load_scene(scene, W, H), W, H, spp, spp_per_wave=spp, stats=bool(os.environ.get("CRT_STATS")),
+                 reference_topology=bool(os.environ.get("CRT_REFTOPO")), exact_visit=bool(os.environ.get("CRT_EXACT")))
 for _ in range(waves):
     r.render(spp)
 r.sync()
 c = r.counters()
-print({k: c[k] for k in ("samples", "extend_rays", "shadow_rays", "node_visits", "tri_tests", "kernel_launches", "render_ms")})
+print(wl, "reftopo" if os.environ.get("CRT_REFTOPO") else "sah", {k: c[k] for k in ("samples", "extend_rays", "shadow_rays", "node_visits", "tri_tests", "kernel_launches", "render_ms")})
 r.close()
