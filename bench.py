@@ -37,13 +37,24 @@ WORKLOADS = {
     "monkeys_1080p": ("monkeys", 1920, 1080, 512),
     "cornell_4k": ("cornell", 3840, 2160, 1024),
     "cornell_256": ("cornell", 256, 256, 16),
+    "terrain1m_1080p": ("terrain707", 1920, 1080, 256),      # BASELINE config 4: 999 700 procedural triangles
+    "terrain131k_1080p": ("terrain256", 1920, 1080, 256),
 }
 SPP_PER_STEP = 64
 L2_BYTES = 126 * 1024 * 1024
 
 
+_SCENE_CACHE = {}
+
+
 def load_scene(name, W, H):
+    """Bundled scenes come from the committed reference dumps; terrainN is generated and built by the product."""
     from cudart_b200 import load_crts
+    if name.startswith("terrain") and name != "terrain64":
+        from cudart_b200.procedural import terrain_scene
+        if name not in _SCENE_CACHE:
+            _SCENE_CACHE[name] = terrain_scene(int(name[len("terrain"):]), W, H)
+        return _SCENE_CACHE[name].with_resolution(W, H)
     return load_crts(os.path.join(ROOT, "tests", "golden", name + ".crts.gz")).with_resolution(W, H)
 
 

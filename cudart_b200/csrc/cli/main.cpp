@@ -1,0 +1,270 @@
+// cudart_b200/csrc/cli/main.cpp - `CudaRT`: the reference's command line on top of the B200 path.
+//
+//   ./CudaRT -f <scene> -s <spp> -w <width> -h <height> [--cpu] [--gpus N] [--dump-scene F] [--no-render] [--metrics F]
+//
+// Same flags, defaults, `../.env` lookup with the `../meshes|settings|textures` fallback, same progress lines and
+// the same three closing lines as the reference's main (main.cpp:24-188); output goes to <scene>.png in the
+// working directory (`-o` is advertised by the reference's usage text but never parsed, D24 - same here).
+// The B200Renderer below is the third implementation of the reference's Renderer seam (renderer.h:78-100):
+// TerminalLauncher::render's call sequence (terminal_launcher.cpp:10-16) drives it unchanged.
+// `--cpu` has no implementation in this repository: it hands over to the unmodified reference binary
+// (oracle/_ref/CudaRT_ref, a reported baseline) when that is present and fails loudly otherwise.
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../../include/crt_abi.h"
+#include "scene_io.h"
+
+using namespace std;
+using namespace std::chrono;
+using namespace crtcli;
+
+namespace {
+
+[[noreturn]] void fatal(const string& what) {          // cuda_error_check.h:15-21 prints and exits
+    cerr << what << endl;
+    exit(1);
+}
+#define CRT(call) do { if ((call) != CRT_OK) fatal(string(#call) + ": " + crt_last_error()); } while (0)
+#define CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) fatal(string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+#define NCCL(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) fatal(string(#call) + ": " + ncclGetErrorString(r_)); } while (0)
+
+// The reference's Renderer contract (renderer.h:78-100) on top of the C ABI; one context per GPU, the image
+// sharded as interleaved row tiles, ONE NCCL all-gather of the compact accumulators when the image is read.
+class B200Renderer {
+public:
+    bool useCuda = true;
+    vector<uint8_t> h_img;                              // Renderer::h_imgPtr: W*H RGBA8
+
+    B200Renderer(const SceneArrays& s, unsigned w, unsigned h, unsigned spp, int gpus) : width(w), height(h), samples(spp) {
+        crt_scene_desc d{};
+        d.tris = s.tris.data(); d.n_tris = (uint32_t)s.tris.size();
+        d.nodes = s.nodes.data(); d.n_nodes = (uint32_t)s.nodes.size();
+        d.mat_floats = s.mat_floats.data(); d.mat_indices = s.mat_indices.data(); d.n_mats = s.n_mats;
+        d.light_indices = s.lights.data(); d.n_lights = (uint32_t)s.lights.size(); d.lights_area = s.lights_area;
+        d.camera = &s.camera;
+        d.tex_data = s.tex_data.data(); d.tex_dims = s.tex_dims.data(); d.tex_offsets = s.tex_offsets.data();
+        d.n_tex = s.n_tex; d.tex_texels = (uint32_t)(s.tex_data.size() / 3);
+        ctx.resize(gpus);
+        streams.resize(gpus);
+        for (int g = 0; g < gpus; g++) {
+            CUDA(cudaSetDevice(g));
+            CUDA(cudaStreamCreateWithFlags(&streams[g], cudaStreamNonBlocking));
+            crt_options o{};
+            o.struct_size = sizeof o;
+            o.device = g; o.rank = (uint32_t)g; o.world = (uint32_t)gpus; o.stream = streams[g];
+            CRT(crt_create(&d, w, h, &o, &ctx[g]));
+        }
+        if (gpus > 1) {
+            comms.resize(gpus);
+            vector<int> devs(gpus);
+            for (int g = 0; g < gpus; g++) devs[g] = g;
+            NCCL(ncclCommInitAll(comms.data(), gpus, devs.data()));
+            size_t padded = 0;
+            void* p = nullptr;
+            CRT(crt_accum_device_ptr(ctx[0], &p, &padded));
+            gathered.resize(gpus);
+            for (int g = 0; g < gpus; g++) {
+                CUDA(cudaSetDevice(g));
+                CUDA(cudaMalloc(&gathered[g], padded * 16 * (size_t)gpus));
+            }
+        }
+        h_img.assign((size_t)w * h * 4, 0);
+    }
+    ~B200Renderer() {
+        for (size_t g = 0; g < ctx.size(); g++) {
+            cudaSetDevice((int)g);
+            if (g < gathered.size() && gathered[g]) cudaFree(gathered[g]);
+            crt_destroy(ctx[g]);
+            if (g < comms.size()) ncclCommDestroy(comms[g]);
+            cudaStreamDestroy(streams[g]);
+        }
+    }
+    void renderOneSamplePerPixel(uint8_t*) { render(1); }
+    void render(unsigned spp) {                          // batch form: `spp` calls of renderOneSamplePerPixel
+        for (crt_ctx* c : ctx) CRT(crt_render(c, spp));  // asynchronous on each GPU's stream
+        samplesRendered += spp;
+    }
+    void copyImageBytes(uint8_t*) {                      // Renderer::copyImageBytes: gather, resolve, gamma
+        if (ctx.size() == 1) { CRT(crt_resolve_rgba8(ctx[0], h_img.data())); return; }
+        size_t padded = 0;
+        NCCL(ncclGroupStart());
+        for (size_t g = 0; g < ctx.size(); g++) {
+            void* p = nullptr;
+            CRT(crt_accum_device_ptr(ctx[g], &p, &padded));
+            NCCL(ncclAllGather(p, gathered[g], padded * 4, ncclFloat, comms[g], streams[g]));
+        }
+        NCCL(ncclGroupEnd());
+        CRT(crt_resolve_gathered(ctx[0], gathered[0], h_img.data(), nullptr));
+        for (size_t g = 1; g < ctx.size(); g++) CRT(crt_sync(ctx[g]));
+    }
+    uint8_t* getImgBytesPointer() { return h_img.data(); }
+    void createMaterialsData() {}
+    unsigned getWidth() const { return width; }
+    unsigned getHeight() const { return height; }
+    int getSamples() const { return (int)samples; }
+    int getSamplesRendered() const { return (int)samplesRendered; }
+    crt_counters counters() {
+        crt_counters total{};
+        for (crt_ctx* c : ctx) {
+            crt_counters k{};
+            CRT(crt_get_counters(c, &k));
+            total.samples += k.samples; total.extend_rays += k.extend_rays; total.shadow_rays += k.shadow_rays;
+            total.kernel_launches += k.kernel_launches; total.render_ms = max(total.render_ms, k.render_ms);
+        }
+        return total;
+    }
+
+private:
+    unsigned width, height, samples;
+    volatile unsigned samplesRendered = 0;
+    vector<crt_ctx*> ctx;
+    vector<cudaStream_t> streams;
+    vector<ncclComm_t> comms;
+    vector<void*> gathered;
+};
+
+// TerminalLauncher::render (terminal_launcher.cpp:10-16), batched: the renderer is told how many samples follow
+// so that it can trace them in large wavefront batches instead of one launch sequence per sample.
+void launch(B200Renderer& r) {
+    uint8_t* img = r.getImgBytesPointer();
+    r.render((unsigned)r.getSamples());
+    r.copyImageBytes(img);
+}
+
+string self_dir() {
+    char buf[4096];
+    const ssize_t n = readlink("/proc/self/exe", buf, sizeof buf - 1);
+    if (n <= 0) return ".";
+    buf[n] = 0;
+    string p(buf);
+    return p.substr(0, p.find_last_of('/'));
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+    int samples = 10, width = 640, height = 480, gpus = 1;
+    string outFile = "out.png", sceneName = "cornell";
+    string objDir, cameraDir, texturePath, dumpScene, metricsFile;
+    const string envPath = "../.env";
+    bool executeOnCpu = false, noRender = false;
+
+    try {
+        EnvFile env(envPath);
+        objDir = env.meshes + "/";
+        cameraDir = env.camera + "/";
+        texturePath = env.textures + "/";
+    } catch (const runtime_error&) {
+        objDir = "../meshes/";
+        cameraDir = "../settings/";
+        texturePath = "../textures/";
+    }
+    string objPath = objDir + sceneName + ".obj", cameraPath = cameraDir + sceneName + "-camera.json";
+
+    if (argc < 2) {
+        cerr << "Usage: CudaRT <options>\n"
+                "-o \t<output file>\n"
+                "-s \t<number of samples>\tdefault:10\n"
+                "-w \t<width>\tdefault:480px\n"
+                "-h \t<height>\tdefault:320px\n"
+                "-f \t<scene>\tdefault: cornell\n"
+                "--cpu \t<flag to run sequential code on CPU only>\tdefault: false\n"
+                "--gpus \t<number of B200s to shard the image over>\tdefault: 1\n";
+        return 1;
+    }
+    vector<string> args(argv + 1, argv + argc);
+    auto value_of = [&](const char* flag, const char* what, int& dst) {
+        auto it = find(args.begin(), args.end(), flag);
+        if (it < args.end() - 1) {
+            try { dst = stoi(*(it + 1)); } catch (invalid_argument&) { cerr << "Invalid argument to " << what << "!" << endl; }
+        }
+    };
+    value_of("-s", "-s", samples);
+    value_of("-w", "-w", width);
+    value_of("-h", "-h", height);
+    value_of("--gpus", "--gpus", gpus);
+    if (find(args.begin(), args.end(), "--cpu") < args.end()) executeOnCpu = true;
+    if (find(args.begin(), args.end(), "--no-render") < args.end()) noRender = true;
+    auto str_of = [&](const char* flag, string& dst) {
+        auto it = find(args.begin(), args.end(), flag);
+        if (it < args.end() - 1) dst = *(it + 1);
+    };
+    str_of("--dump-scene", dumpScene);
+    str_of("--metrics", metricsFile);
+    if (find(args.begin(), args.end(), "-f") < args.end() - 1) {
+        sceneName = *(find(args.begin(), args.end(), "-f") + 1);
+        objPath = objDir + sceneName + ".obj";
+        cameraPath = cameraDir + sceneName + "-camera.json";
+        outFile = sceneName + ".png";
+    }
+
+    if (executeOnCpu) {
+        // The CPU path is the reference's own; this repository ships no CPU renderer and no fallback.
+        const string ref = self_dir() + "/../oracle/_ref/CudaRT_ref";
+        if (access(ref.c_str(), X_OK) != 0) fatal("--cpu: the reference binary " + ref + " is not built here (make -C oracle ref); the B200 path has no CPU fallback");
+        execv(ref.c_str(), argv);
+        fatal("--cpu: cannot exec " + ref);
+    }
+
+    cout << "Samples: " << samples << endl
+         << "Width: " << width << endl
+         << "Height: " << height << endl
+         << "Obj path: " << objPath << endl
+         << "Camera path: " << cameraPath << endl
+         << "Output: " << outFile << endl;
+
+    SceneArrays scene;
+    try {
+        cout << "Loading single .obj as scene from " << objPath << endl;
+        const ObjFile obj = load_obj(objPath);
+        const crt::RefCamera cam = load_camera_json(cameraPath, (unsigned)width, (unsigned)height);
+        scene = assemble_scene(obj, cam, texturePath);
+    } catch (const exception& e) {
+        fatal(string("terminate called after throwing an instance of 'std::runtime_error'\n  what():  ") + e.what());
+    }
+    for (size_t i = 0; i < scene.mesh_report.size(); i++)
+        cout << "Mesh " << i << ": `" << scene.mesh_report[i].first << "`" << endl
+             << "\t" << scene.mesh_report[i].second << " vertices | \t" << scene.mesh_report[i].second / 3 << " triangles" << endl;
+    cout << "Total number of triangles:\t" << scene.tris.size() << endl;
+    cout << "\nLaunching CudaRT version 0.1.0" << endl;
+    if (!dumpScene.empty()) save_crts(dumpScene, scene, (unsigned)width, (unsigned)height);
+    if (noRender) return 0;
+
+    int devices = 0;
+    cudaGetDeviceCount(&devices);
+    cout << "Got " << devices << " CUDA-capable devices" << endl;
+    if (devices == 0) fatal("no CUDA device: the B200 path has no CPU fallback (use --cpu for the reference's own CPU renderer)");
+    gpus = max(1, min(gpus, devices));
+
+    B200Renderer renderer(scene, (unsigned)width, (unsigned)height, (unsigned)samples, gpus);
+    auto start = high_resolution_clock::now();
+    launch(renderer);
+    auto stop = high_resolution_clock::now();
+    write_png_rgba8(outFile, renderer.h_img.data(), (unsigned)width, (unsigned)height);     // Launcher::saveToImage
+
+    const float elapsedTime = duration_cast<microseconds>(stop - start).count() / 1000000.0f;
+    const int samplesRendered = renderer.getSamplesRendered();
+    cout << "Rendered to " << outFile << " for " << samplesRendered << " samples per pixel. " << endl;
+    cout << "Elapsed time in seconds = " << elapsedTime << endl;
+    cout << "Average samples per pixel = " << samplesRendered / elapsedTime << endl;
+    if (!metricsFile.empty()) {
+        const crt_counters c = renderer.counters();
+        ofstream m(metricsFile);
+        m << "{\"scene\": \"" << sceneName << "\", \"width\": " << width << ", \"height\": " << height << ", \"spp\": " << samplesRendered
+          << ", \"gpus\": " << gpus << ", \"seconds\": " << elapsedTime << ", \"msamples_per_s\": " << c.samples / elapsedTime / 1e6
+          << ", \"mrays_per_s\": " << (c.extend_rays + c.shadow_rays) / elapsedTime / 1e6 << ", \"kernel_launches\": " << c.kernel_launches
+          << ", \"device_render_ms\": " << c.render_ms << "}" << endl;
+    }
+    return 0;
+}

@@ -1,0 +1,558 @@
+// cudart_b200/csrc/cli/scene_io.cpp - see scene_io.h.  No CUDA here; BVH and light list come through the C ABI.
+#include "scene_io.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <sstream>
+
+#include "../../../include/crt_abi.h"
+
+namespace crtcli {
+namespace {
+
+[[noreturn]] void die(const std::string& what) { throw std::runtime_error(what); }
+
+// ---- line helpers with the reference parser's token rules (obj_load.h:330-402) -------------------
+std::string first_token(const std::string& in) {
+    const size_t a = in.find_first_not_of(" \t");
+    if (in.empty() || a == std::string::npos) return "";
+    const size_t b = in.find_first_of(" \t", a);
+    return b == std::string::npos ? in.substr(a) : in.substr(a, b - a);
+}
+std::string tail_of(const std::string& in) {
+    const size_t a = in.find_first_not_of(" \t");
+    const size_t sp = in.find_first_of(" \t", a);
+    const size_t b = in.find_first_not_of(" \t", sp);
+    const size_t e = in.find_last_not_of(" \t");
+    if (b == std::string::npos) return "";
+    return e == std::string::npos ? in.substr(b) : in.substr(b, e - b + 1);
+}
+// Splits on a one-character separator; an empty field between two separators is kept (that is how "1//3" yields
+// an empty texture index), a separator right after a non-empty field is consumed.
+std::vector<std::string> split_on(const std::string& in, char sep) {
+    std::vector<std::string> out;
+    std::string cur;
+    for (size_t i = 0; i < in.size(); i++) {
+        if (in[i] == sep) {
+            if (!cur.empty()) { out.push_back(cur); cur.clear(); }
+            else out.push_back("");
+        } else if (i + 1 >= in.size()) {
+            cur += in[i];
+            out.push_back(cur);
+            break;
+        } else {
+            cur += in[i];
+        }
+    }
+    return out;
+}
+template <class T>
+const T& element_at(const std::vector<T>& v, const std::string& index) {      // 1-based, negative = from the end
+    int idx = std::stoi(index);
+    idx = idx < 0 ? (int)v.size() + idx : idx - 1;
+    if (idx < 0 || idx >= (int)v.size()) die("OBJ index out of range: " + index);
+    return v[(size_t)idx];
+}
+
+bool file_exists(const std::string& p) { return std::ifstream(p.c_str()).good(); }
+
+// ---- a small JSON reader (the camera file is one flat object of numbers, strings and number arrays) -----
+struct Json {
+    enum Kind { Null, Num, Str, Arr, Obj, Bool } kind = Null;
+    double num = 0;
+    std::string str;
+    std::vector<Json> arr;
+    std::vector<std::pair<std::string, Json>> obj;
+    const Json& at(const std::string& k) const {
+        for (auto& kv : obj) if (kv.first == k) return kv.second;
+        die("camera JSON: missing key \"" + k + "\"");
+    }
+};
+struct JsonParser {
+    const std::string& s;
+    size_t i = 0;
+    void ws() { while (i < s.size() && std::isspace((unsigned char)s[i])) i++; }
+    Json value() {
+        ws();
+        if (i >= s.size()) die("camera JSON: unexpected end");
+        Json j;
+        const char c = s[i];
+        if (c == '{') {
+            j.kind = Json::Obj; i++; ws();
+            if (s[i] == '}') { i++; return j; }
+            for (;;) {
+                ws();
+                Json k = value();
+                if (k.kind != Json::Str) die("camera JSON: object key must be a string");
+                ws();
+                if (s[i++] != ':') die("camera JSON: ':' expected");
+                j.obj.emplace_back(k.str, value());
+                ws();
+                if (s[i] == ',') { i++; continue; }
+                if (s[i] == '}') { i++; return j; }
+                die("camera JSON: ',' or '}' expected");
+            }
+        }
+        if (c == '[') {
+            j.kind = Json::Arr; i++; ws();
+            if (s[i] == ']') { i++; return j; }
+            for (;;) {
+                j.arr.push_back(value());
+                ws();
+                if (s[i] == ',') { i++; continue; }
+                if (s[i] == ']') { i++; return j; }
+                die("camera JSON: ',' or ']' expected");
+            }
+        }
+        if (c == '"') {
+            j.kind = Json::Str; i++;
+            while (i < s.size() && s[i] != '"') { if (s[i] == '\\' && i + 1 < s.size()) i++; j.str += s[i++]; }
+            i++;
+            return j;
+        }
+        if (!s.compare(i, 4, "true")) { j.kind = Json::Bool; j.num = 1; i += 4; return j; }
+        if (!s.compare(i, 5, "false")) { j.kind = Json::Bool; i += 5; return j; }
+        if (!s.compare(i, 4, "null")) { i += 4; return j; }
+        char* end = nullptr;
+        j.kind = Json::Num;
+        j.num = std::strtod(s.c_str() + i, &end);           // picojson parses numbers with strtod as well
+        if (end == s.c_str() + i) die("camera JSON: bad value");
+        i = (size_t)(end - s.c_str());
+        return j;
+    }
+};
+
+float len3(const crt::F3& v) { return sqrtf(v.x * v.x + v.y * v.y + v.z * v.z); }
+crt::F3 norm3(const crt::F3& v) { const float n = len3(v); return {v.x / n, v.y / n, v.z / n}; }
+crt::F3 cross3(const crt::F3& a, const crt::F3& b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+crt::F3 vec_from(const Json& a) {
+    if (a.kind != Json::Arr || a.arr.size() < 3) die("camera JSON: 3-vector expected");
+    return {(float)a.arr[0].num, (float)a.arr[1].num, (float)a.arr[2].num};
+}
+
+}  // namespace
+
+// ---- .env (env_loader.cpp:14-37) ------------------------------------------------------------------------
+EnvFile::EnvFile(const std::string& path) {
+    std::ifstream f(path);
+    if (!f.is_open()) die("Error opening " + path);
+    const std::string keys[3] = {"MESHES_PATH", "CAMERA_PATH", "TEXTURES_PATH"};
+    std::string* slots[3] = {&meshes, &camera, &textures};
+    std::string line;
+    while (std::getline(f, line)) {
+        if (!line.empty() && (line[0] == '#' || line[0] == '\n')) continue;
+        for (int k = 0; k < 3; k++)
+            if (line.find(keys[k]) != std::string::npos) {      // the value is whatever follows KEY plus one character
+                *slots[k] = line.size() > keys[k].size() + 1 ? line.substr(keys[k].size() + 1) : "";
+                break;
+            }
+    }
+}
+
+// ---- camera (json_loader.cpp:25-47) ---------------------------------------------------------------------
+crt::RefCamera load_camera_json(const std::string& path, unsigned width, unsigned height) {
+    if (!file_exists(path)) die("File " + path + " not found.");
+    std::ifstream f(path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string text = ss.str();
+    JsonParser p{text};
+    const Json root = p.value();
+    if (root.kind != Json::Obj) die("camera JSON: object expected loading camera!");
+    const float fov_deg = (float)root.at("fieldOfView").num;
+    const float focal = (float)root.at("focalLength").num;
+    const float fstop = (float)root.at("fStop").num;
+    crt::RefCamera c{};
+    c.xpixels = (int32_t)width;
+    c.ypixels = (int32_t)height;
+    c.fov = tanf(fov_deg * 0.5f * M_PI / 180.0f);
+    c.eye = vec_from(root.at("eye"));
+    const crt::F3 dir = vec_from(root.at("viewDirection"));
+    c.focusDistance = len3(dir);
+    c.dir = norm3(dir);
+    c.up = norm3(vec_from(root.at("upDirection")));
+    c.right = norm3(cross3(c.dir, c.up));
+    c.apertureWidth = focal / fstop;
+    c.aspect = (float)width / (float)height;
+    return c;
+}
+
+// ---- OBJ / MTL (obj_load.h:441-723, 1016-1186) ------------------------------------------------------------
+namespace {
+void load_mtl(const std::string& path, std::vector<ObjMaterial>& out) {
+    if (path.size() < 4 || path.substr(path.size() - 4) != ".mtl") return;
+    std::ifstream f(path);
+    if (!f.is_open()) return;
+    ObjMaterial cur;
+    bool open = false;
+    std::string line;
+    auto triple = [](const std::string& l, float* dst) {
+        const std::vector<std::string> t = split_on(tail_of(l), ' ');
+        if (t.size() != 3) return;
+        for (int k = 0; k < 3; k++) dst[k] = std::stof(t[k]);
+    };
+    while (std::getline(f, line)) {
+        const std::string key = first_token(line);
+        if (key == "newmtl") {
+            if (open) { out.push_back(cur); cur = ObjMaterial(); }
+            open = true;
+            cur.name = line.size() > 7 ? tail_of(line) : "none";
+        }
+        if (key == "Ka") triple(line, cur.Ka);
+        if (key == "Kd") triple(line, cur.Kd);
+        if (key == "Ks") triple(line, cur.Ks);
+        if (key == "Ns") cur.Ns = std::stof(tail_of(line));
+        if (key == "Ni") cur.Ni = std::stof(tail_of(line));
+        if (key == "map_Kd") cur.map_Kd = tail_of(line);
+        if (key == "type") cur.type = tail_of(line);                  // CudaRT-specific keys (obj_load.h:1161-1170)
+        if (key == "diffuse") cur.diffuse = std::stof(tail_of(line));
+    }
+    out.push_back(cur);
+}
+}  // namespace
+
+ObjFile load_obj(const std::string& path) {
+    ObjFile out;
+    if (path.size() < 4 || path.substr(path.size() - 4) != ".obj") die("Failed to load mesh for " + path);
+    std::ifstream f(path);
+    if (!f.is_open()) die("Failed to load mesh for " + path);
+    std::vector<std::array<float, 3>> pos, nor;
+    std::vector<std::array<float, 2>> tex;
+    std::vector<std::string> mesh_mat_names;
+    std::vector<ObjVertex> cur;
+    std::string meshname, line;
+    bool listening = false;
+    auto close_mesh = [&](const std::string& name) {
+        ObjMesh m;
+        m.name = name;
+        m.vertices.swap(cur);
+        out.meshes.push_back(std::move(m));
+    };
+    while (std::getline(f, line)) {
+        const std::string key = first_token(line);
+        if (key == "o" || key == "g" || (!line.empty() && line[0] == 'g')) {
+            const std::string name = (key == "o" || key == "g") ? tail_of(line) : "unnamed";
+            if (!listening) listening = true;
+            else if (!cur.empty()) close_mesh(meshname);
+            meshname = name;
+        }
+        if (key == "v" || key == "vn") {
+            const std::vector<std::string> t = split_on(tail_of(line), ' ');
+            if (t.size() < 3) die("OBJ: malformed line: " + line);
+            (key == "v" ? pos : nor).push_back({std::stof(t[0]), std::stof(t[1]), std::stof(t[2])});
+        }
+        if (key == "vt") {
+            const std::vector<std::string> t = split_on(tail_of(line), ' ');
+            if (t.size() < 2) die("OBJ: malformed line: " + line);
+            tex.push_back({std::stof(t[0]), std::stof(t[1])});
+        }
+        if (key == "f") {
+            const std::vector<std::string> corners = split_on(tail_of(line), ' ');
+            if (corners.size() != 3)
+                die("OBJ: only triangulated faces are supported (the reference counts three vertices per face, scene.h:27-29): " + line);
+            ObjVertex v[3];
+            bool no_normal = false;
+            for (int k = 0; k < 3; k++) {
+                const std::vector<std::string> idx = split_on(corners[k], '/');
+                const auto& p = element_at(pos, idx.at(0));
+                std::memcpy(v[k].p, p.data(), 12);
+                if (idx.size() >= 2 && !idx[1].empty()) { const auto& t = element_at(tex, idx[1]); v[k].t[0] = t[0]; v[k].t[1] = t[1]; }
+                if (idx.size() == 3) { const auto& n = element_at(nor, idx[2]); std::memcpy(v[k].n, n.data(), 12); }
+                else no_normal = true;
+            }
+            if (no_normal) {          // face normal from the corner positions (obj_load.h:836-847)
+                const float a[3] = {v[0].p[0] - v[1].p[0], v[0].p[1] - v[1].p[1], v[0].p[2] - v[1].p[2]};
+                const float b[3] = {v[2].p[0] - v[1].p[0], v[2].p[1] - v[1].p[1], v[2].p[2] - v[1].p[2]};
+                const float n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+                for (auto& vv : v) std::memcpy(vv.n, n, 12);
+            }
+            for (auto& vv : v) { cur.push_back(vv); out.all_vertices.push_back(vv); }
+        }
+        if (key == "usemtl") {
+            mesh_mat_names.push_back(tail_of(line));
+            if (!cur.empty()) close_mesh(meshname + "_2");          // material change inside a group starts a new mesh
+        }
+        if (key == "mtllib") {
+            const size_t slash = path.find_last_of('/');
+            load_mtl((slash == std::string::npos ? std::string() : path.substr(0, slash + 1)) + tail_of(line), out.materials);
+        }
+    }
+    if (!cur.empty()) close_mesh(meshname);
+    // mesh i takes the material named by the i-th `usemtl` (obj_load.h:698-713, D25)
+    for (size_t i = 0; i < mesh_mat_names.size() && i < out.meshes.size(); i++)
+        for (const ObjMaterial& m : out.materials)
+            if (m.name == mesh_mat_names[i]) { out.meshes[i].material = m; break; }
+    if (out.meshes.empty()) die("Failed to load mesh for " + path);
+    return out;
+}
+
+// ---- PNG in / out ---------------------------------------------------------------------------------------------
+namespace {
+uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+int paeth(int a, int b, int c) {
+    const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+}  // namespace
+
+Texture load_png_as_float3(const std::string& path) {
+    if (!file_exists(path)) die("File " + path + " not found.");
+    std::ifstream f(path, std::ios::binary);
+    std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    if (buf.size() < 33 || std::memcmp(buf.data(), sig, 8)) die(path + ": not a PNG file");
+    unsigned w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, plte;
+    for (size_t off = 8; off + 12 <= buf.size();) {
+        const uint32_t len = be32(&buf[off]);
+        const std::string tag((const char*)&buf[off + 4], 4);
+        const uint8_t* data = &buf[off + 8];
+        if (off + 12 + len > buf.size()) die(path + ": truncated PNG");
+        if (tag == "IHDR") { w = be32(data); h = be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12]; }
+        else if (tag == "PLTE") plte.assign(data, data + len);
+        else if (tag == "IDAT") idat.insert(idat.end(), data, data + len);
+        else if (tag == "IEND") break;
+        off += 12 + len;
+    }
+    const int ch = ctype == 2 ? 3 : ctype == 6 ? 4 : ctype == 3 ? 1 : 0;
+    if (!w || !h || depth != 8 || !ch || interlace) die(path + ": only 8-bit non-interlaced RGB / RGBA / palette PNGs are supported");
+    const size_t stride = (size_t)w * ch;
+    std::vector<uint8_t> raw((stride + 1) * h);
+    uLongf rawlen = (uLongf)raw.size();
+    if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) die(path + ": bad PNG data");
+    std::vector<uint8_t> px(stride * h);
+    for (unsigned y = 0; y < h; y++) {
+        const uint8_t ft = raw[(stride + 1) * y];
+        const uint8_t* in = &raw[(stride + 1) * y + 1];
+        uint8_t* row = &px[stride * y];
+        const uint8_t* up = y ? &px[stride * (y - 1)] : nullptr;
+        for (size_t x = 0; x < stride; x++) {
+            const int a = x >= (size_t)ch ? row[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)ch) ? up[x - ch] : 0;
+            int v = in[x];
+            switch (ft) {
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) >> 1; break;
+                case 4: v += paeth(a, b, c); break;
+                default: die(path + ": bad PNG filter");
+            }
+            row[x] = (uint8_t)v;
+        }
+    }
+    Texture t;
+    t.w = w;
+    t.h = h;
+    t.rgb.resize((size_t)w * h * 3);
+    // stbi_loadf on an LDR file: channel -> pow(v / 255, 2.2) (stb_image.h:1671-1690, compiled as C++: the float pow)
+    float lut[256];
+    for (int v = 0; v < 256; v++) lut[v] = (float)(std::pow(v / 255.0f, 2.2f) * 1.0f);
+    for (size_t i = 0; i < (size_t)w * h; i++)
+        for (int k = 0; k < 3; k++) {
+            uint8_t v;
+            if (ctype == 3) { const size_t e = (size_t)px[i] * 3 + k; v = e < plte.size() ? plte[e] : 0; }
+            else v = px[i * ch + k];
+            t.rgb[3 * i + k] = lut[v];
+        }
+    return t;
+}
+
+void write_png_rgba8(const std::string& path, const uint8_t* rgba, unsigned w, unsigned h) {
+    std::vector<uint8_t> raw(((size_t)w * 4 + 1) * h);
+    for (unsigned y = 0; y < h; y++) {
+        raw[((size_t)w * 4 + 1) * y] = 0;
+        std::memcpy(&raw[((size_t)w * 4 + 1) * y + 1], rgba + (size_t)w * 4 * y, (size_t)w * 4);
+    }
+    uLongf clen = compressBound((uLong)raw.size());
+    std::vector<uint8_t> comp(clen);
+    if (compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), 6) != Z_OK) die("PNG compression failed");
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) die("cannot write " + path);
+    auto chunk = [&](const char* tag, const uint8_t* data, uint32_t len) {
+        uint8_t hdr[8] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len,
+                          (uint8_t)tag[0], (uint8_t)tag[1], (uint8_t)tag[2], (uint8_t)tag[3]};
+        uLong crc = crc32(0L, hdr + 4, 4);
+        if (len) crc = crc32(crc, data, len);
+        const uint8_t tailb[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+        std::fwrite(hdr, 1, 8, f);
+        if (len) std::fwrite(data, 1, len, f);
+        std::fwrite(tailb, 1, 4, f);
+    };
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    std::fwrite(sig, 1, 8, f);
+    const uint8_t ihdr[13] = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w,
+                              (uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h, 8, 6, 0, 0, 0};
+    chunk("IHDR", ihdr, 13);
+    chunk("IDAT", comp.data(), (uint32_t)clen);
+    chunk("IEND", nullptr, 0);
+    std::fclose(f);
+}
+
+// ---- scene assembly (scene.cpp:55-203) ------------------------------------------------------------------------
+namespace {
+enum { DIFFUSE = 0, SPECULAR, DIFFSPEC, MICROFACET, REFRACTIVE, EMISSIVE };
+
+struct Mat {                                         // material.h:17-55
+    int bsdf = DIFFUSE;
+    float kd[3] = {0, 0, 0}, ka[3] = {0, 0, 0}, ks[3] = {0, 0, 0};
+    float ns = 0.f, ni = 1.f, diffuse = 1.f;
+    int tex = -1;
+};
+// The reference's float3 operator!= is true only when ALL three components differ (linalg.h:12), so its
+// Material::operator== calls two materials equal unless some colour differs in every component (D10).
+bool all_components_differ(const float* a, const float* b) { return a[0] != b[0] && a[1] != b[1] && a[2] != b[2]; }
+bool ref_equal(const Mat& a, const Mat& b) {
+    if (a.bsdf != b.bsdf) return false;
+    if (all_components_differ(a.kd, b.kd) || all_components_differ(a.ka, b.ka) || all_components_differ(a.ks, b.ks)) return false;
+    return !(a.ns != b.ns) && !(a.ni != b.ni) && !(a.diffuse != b.diffuse);
+}
+// material.h:57-79 - not a strict weak ordering (D11); the map built with it decides the material ids.
+struct RefLess {
+    bool operator()(const Mat& l, const Mat& r) const {
+        if (l.bsdf != r.bsdf) return l.bsdf < r.bsdf;
+        if (l.kd[0] < r.kd[0] || l.kd[1] < r.kd[1] || l.kd[2] < r.kd[2]) return true;
+        if (l.ka[0] < r.ka[0] || l.ka[1] < r.ka[1] || l.ka[2] < r.ka[2]) return true;
+        if (l.ks[0] < r.ks[0] || l.ks[1] < r.ks[1] || l.ks[2] < r.ks[2]) return true;
+        if (l.ns < r.ns) return true;
+        if (l.ni < r.ni) return true;
+        return false;
+    }
+};
+Mat from_mtl(const ObjMaterial& m) {                 // scene.cpp:175-190
+    static const std::map<std::string, int> kinds = {{"LAMBERT", DIFFUSE}, {"SPECULAR", SPECULAR}, {"DIFFSPEC", DIFFSPEC},
+                                                     {"MICROFACET", MICROFACET}, {"REFRACTIVE", REFRACTIVE}, {"EMISSIVE", EMISSIVE}};
+    Mat o;
+    for (int k = 0; k < 3; k++) { o.ka[k] = m.Ka[k] * 3.0f; o.kd[k] = m.Kd[k]; o.ks[k] = m.Ks[k]; }   // LIGHTS_GAIN 3
+    o.ns = m.Ns; o.ni = m.Ni; o.diffuse = m.diffuse;
+    const auto it = kinds.find(m.type);
+    o.bsdf = it == kinds.end() ? DIFFUSE : it->second;
+    return o;
+}
+}  // namespace
+
+SceneArrays assemble_scene(const ObjFile& obj, const crt::RefCamera& cam, const std::string& textures_dir) {
+    SceneArrays s;
+    s.camera = cam;
+    // textures: every distinct map_Kd of the MTL file, in file order (scene.cpp:55-71, texture_store.cpp:37-71)
+    std::vector<std::string> tex_files;
+    for (const ObjMaterial& m : obj.materials)
+        if (!m.map_Kd.empty() && std::find(tex_files.begin(), tex_files.end(), m.map_Kd) == tex_files.end()) tex_files.push_back(m.map_Kd);
+    s.n_tex = (uint32_t)tex_files.size();
+    s.tex_offsets.push_back(0);
+    uint32_t total = 0, last_w = 0;
+    for (const std::string& file : tex_files) {
+        const Texture t = load_png_as_float3(textures_dir + file);
+        std::cout << "Loading " << textures_dir + file << ": not hdr." << std::endl;
+        s.tex_dims.push_back(t.w);
+        s.tex_dims.push_back(t.h);
+        s.tex_data.insert(s.tex_data.end(), t.rgb.begin(), t.rgb.end());
+        total += t.w * t.h;
+        s.tex_offsets.push_back(total);
+        last_w = t.w;
+    }
+    s.tex_data.resize(s.tex_data.size() + 3 * (size_t)last_w, 0.f);        // zero padding: one row of the last texture
+    if (s.n_tex == 0) s.tex_offsets.clear();   // the reference crashes without textures (D14); the new path just has none
+
+    // material table: ids in first-seen order through the reference's map + find (scene.cpp:80-103, 192-203)
+    std::map<Mat, unsigned, RefLess> ids;
+    unsigned next = 0;
+    for (const ObjMesh& m : obj.meshes) {
+        const Mat mm = from_mtl(m.material);
+        if (ids.count(mm) == 0) { ids.insert({mm, next}); next++; }
+    }
+    s.n_mats = (uint32_t)ids.size();
+    std::vector<Mat> table(s.n_mats);
+    for (const auto& kv : ids)
+        if (kv.second < s.n_mats) table[kv.second] = kv.first;
+    const std::vector<Mat> lookup = table;
+
+    size_t n_tris = 0;
+    for (const ObjMesh& m : obj.meshes) n_tris += m.vertices.size() / 3;
+    s.tris.resize(n_tris);
+    std::memset(s.tris.data(), 0, n_tris * sizeof(crt::RefTriangle));
+    std::vector<float> positions;
+    positions.reserve(9 * n_tris);
+    uint32_t tri_id = 0;
+    for (const ObjMesh& m : obj.meshes) {
+        const Mat mm = from_mtl(m.material);
+        const auto it = std::find_if(lookup.begin(), lookup.end(), [&](const Mat& x) { return ref_equal(x, mm); });
+        if (it == lookup.end()) die("material of mesh `" + m.name + "` is not in the material table");
+        const uint32_t mat_id = (uint32_t)(it - lookup.begin());
+        if (!m.material.map_Kd.empty()) {
+            const auto tf = std::find(tex_files.begin(), tex_files.end(), m.material.map_Kd);
+            if (tf != tex_files.end()) table[mat_id].tex = (int)(tf - tex_files.begin());
+        }
+        s.mesh_report.emplace_back(m.name, m.vertices.size());
+        for (size_t i = 0; i + 2 < m.vertices.size(); i += 3) {       // scene.cpp:106-134
+            const ObjVertex &a = m.vertices[i], &b = m.vertices[i + 1], &c = m.vertices[i + 2];
+            crt::RefTriangle& t = s.tris[tri_id];
+            t.v1 = {a.p[0], a.p[1], a.p[2]};
+            t.n1 = {a.n[0], a.n[1], a.n[2]}; t.n2 = {b.n[0], b.n[1], b.n[2]}; t.n3 = {c.n[0], c.n[1], c.n[2]};
+            t.uv1 = {a.t[0], a.t[1]}; t.uv2 = {b.t[0], b.t[1]}; t.uv3 = {c.t[0], c.t[1]};
+            t.e1 = {b.p[0] - a.p[0], b.p[1] - a.p[1], b.p[2] - a.p[2]};
+            t.e2 = {c.p[0] - a.p[0], c.p[1] - a.p[1], c.p[2] - a.p[2]};
+            t.materialId = mat_id;
+            t.area = len3(cross3(t.e1, t.e2)) / 2.0f;
+            t.triId = tri_id++;
+        }
+    }
+    for (const ObjVertex& v : obj.all_vertices) positions.insert(positions.end(), v.p, v.p + 3);
+    if (positions.size() != 9 * n_tris) die("internal: vertex soup and triangle count disagree");
+
+    s.mat_floats.resize(12 * (size_t)s.n_mats);
+    s.mat_indices.resize(2 * (size_t)s.n_mats);
+    for (uint32_t m = 0; m < s.n_mats; m++) {              // sequential_renderer.cu:48-64
+        float* f = &s.mat_floats[12 * m];
+        std::memcpy(f, table[m].kd, 12); std::memcpy(f + 3, table[m].ka, 12); std::memcpy(f + 6, table[m].ks, 12);
+        f[9] = table[m].ns; f[10] = table[m].ni; f[11] = table[m].diffuse;
+        s.mat_indices[2 * m] = table[m].bsdf;
+        s.mat_indices[2 * m + 1] = table[m].tex;
+    }
+    // BVH + light list: the product's host scene build, through the C ABI
+    s.nodes.resize(std::max<size_t>(2 * n_tris, 1));
+    uint32_t n_nodes = 0;
+    if (crt_build_bvh(s.tris.data(), positions.data(), (uint32_t)n_tris, s.nodes.data(), &n_nodes) != CRT_OK) die(crt_last_error());
+    s.nodes.resize(n_nodes);
+    std::cout << "Total BVH Nodes: " << n_nodes << std::endl;
+    s.lights.resize(std::max<size_t>(n_tris, 1));
+    uint32_t n_lights = 0;
+    if (crt_build_lights(s.tris.data(), (uint32_t)n_tris, s.mat_floats.data(), s.mat_indices.data(), s.n_mats, s.lights.data(),
+                         &n_lights, &s.lights_area) != CRT_OK)
+        die(crt_last_error());
+    s.lights.resize(n_lights);
+    return s;
+}
+
+void save_crts(const std::string& path, const SceneArrays& s, unsigned width, unsigned height) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) die("cannot write " + path);
+    uint32_t hdr[16] = {0};
+    std::memcpy(&hdr[0], "CRTS", 4);
+    hdr[1] = 1; hdr[2] = (uint32_t)s.tris.size(); hdr[3] = (uint32_t)s.nodes.size(); hdr[4] = s.n_mats;
+    hdr[5] = (uint32_t)s.lights.size(); hdr[6] = s.n_tex; hdr[7] = (uint32_t)(s.tex_data.size() / 3); hdr[8] = width; hdr[9] = height;
+    std::memcpy(&hdr[10], &s.lights_area, 4);
+    auto put = [&](const void* p, size_t n) { if (n && std::fwrite(p, 1, n, f) != n) die("write failed: " + path); };
+    put(hdr, sizeof hdr);
+    put(&s.camera, sizeof s.camera);
+    put(s.tris.data(), s.tris.size() * sizeof(crt::RefTriangle));
+    put(s.nodes.data(), s.nodes.size() * sizeof(crt::RefNode));
+    put(s.mat_floats.data(), s.mat_floats.size() * 4);
+    put(s.mat_indices.data(), s.mat_indices.size() * 4);
+    put(s.lights.data(), s.lights.size() * 4);
+    put(s.tex_dims.data(), s.tex_dims.size() * 4);
+    if (s.n_tex) put(s.tex_offsets.data(), s.tex_offsets.size() * 4);
+    else { const uint32_t zero = 0; put(&zero, 4); }
+    put(s.tex_data.data(), s.tex_data.size() * 4);
+    std::fclose(f);
+}
+
+}  // namespace crtcli

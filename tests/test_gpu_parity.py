@@ -265,3 +265,51 @@ def test_errors_are_codes_not_crashes(golden, B200Renderer):
     bad = dataclasses.replace(fs, light_indices=np.array([10 ** 6], np.uint32))
     with pytest.raises(capi.CrtError):
         B200Renderer(bad, 16, 16)
+
+
+def _read_png_rgba(path):
+    import struct
+    import zlib
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    off, idat, w, h = 8, b"", 0, 0
+    while off < len(data):
+        n, tag = struct.unpack(">I4s", data[off:off + 8])
+        body = data[off + 8:off + 8 + n]
+        if tag == b"IHDR":
+            w, h, depth, ctype = struct.unpack(">IIBB", body[:10])
+            assert (depth, ctype) == (8, 6)
+        elif tag == b"IDAT":
+            idat += body
+        off += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 4 * w)
+    assert not raw[:, 0].any()                       # the writer uses filter type 0 on every row
+    return raw[:, 1:].reshape(h, w, 4)
+
+
+def test_command_line_end_to_end_writes_the_same_png(tmp_path, B200Renderer):
+    """`./CudaRT -f tiny -s 8 -w 40 -h 30` (reference CLI surface, ../.env lookup, <scene>.png in the cwd, the three
+    closing lines of main.cpp:183-185) produces exactly the bytes the Renderer seam produces."""
+    import os
+    import subprocess
+    from cudart_b200 import load_crts
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tiny = os.path.join(root, "tests", "golden", "tiny")
+    (tmp_path / "build").mkdir()
+    (tmp_path / ".env").write_text("MESHES_PATH=%s/meshes\nCAMERA_PATH=%s/settings\nTEXTURES_PATH=%s/textures\n" % (tiny, tiny, tiny))
+    p = subprocess.run([os.path.join(root, "cudart_b200", "CudaRT"), "-f", "tiny", "-s", "8", "-w", "40", "-h", "30",
+                        "--metrics", str(tmp_path / "m.json")], cwd=tmp_path / "build", capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    for line in ("Rendered to tiny.png for 8 samples per pixel.", "Elapsed time in seconds = ", "Average samples per pixel = "):
+        assert line in p.stdout
+    png = _read_png_rgba(tmp_path / "build" / "tiny.png")
+    fs = load_crts(os.path.join(root, "tests", "golden", "tiny.crts.gz"))
+    r = B200Renderer(fs, 40, 30, 8)
+    r.render(8)
+    r.copyImageBytes()
+    assert np.array_equal(png, r.h_imgPtr)
+    assert np.array_equal(png, orc.resolve_rgba8(r.accum(), 8))
+    r.close()
+    import json
+    m = json.load(open(tmp_path / "m.json"))
+    assert m["spp"] == 8 and m["msamples_per_s"] > 0 and m["kernel_launches"] > 0
