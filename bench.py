@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--workload", default="cornellSphere_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--spp-per-step", type=int, default=SPP_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spp-per-wave", type=int, default=0, help="samples per pixel per wavefront batch (0 = auto, ~4M paths)")
     args = ap.parse_args()
     scene, W, H, total_spp = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -224,7 +225,8 @@ def main():
     fs = load_scene(scene, W, H)
     spp_step = args.spp_per_step * world                      # weak scaling: per-GPU work fixed
     stream = torch.cuda.current_stream().cuda_stream
-    r = B200Renderer(fs, W, H, total_spp, device=local, rank=rank, world=world, profile=True, stream=stream)
+    r = B200Renderer(fs, W, H, total_spp, device=local, rank=rank, world=world, profile=True, stream=stream,
+                     spp_per_wave=args.spp_per_wave)
 
     def barrier():
         if world > 1:
@@ -265,9 +267,12 @@ def main():
     stage = {k: round(c1["stage_ms"][k] - c0["stage_ms"][k], 3) for k in c1["stage_ms"]}
     r.close()
 
-    # ---- e2e through the public API with host buffers: upload + render + RGBA8 readback every step ----
+    # ---- e2e through the public API with HOST buffers: every step uploads the scene (host -> device), renders
+    # spp_step samples per pixel and reads the RGBA8 frame back (device -> host), like one frame of an animation ----
+    rr = B200Renderer(fs, W, H, spp_step, device=local, rank=rank, world=world, stream=stream, spp_per_wave=args.spp_per_wave)
+
     def e2e_step():
-        rr = B200Renderer(fs, W, H, spp_step, device=local, rank=rank, world=world, stream=stream)
+        rr.update_scene(fs)
         rr.render(spp_step)
         if world > 1:
             g = gather_framebuffer(rr)
@@ -275,7 +280,6 @@ def main():
                 rr.resolve_gathered(g.data_ptr(), want_rgba8=True)
         else:
             rr.copyImageBytes()
-        rr.close()
 
     e2e_step()
     barrier()
@@ -287,11 +291,12 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = samples / float(e2e_s.item()) / 1e6
+    rr.close()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         a_ray, od = algorithmic_bytes(scene, W, H)
-        n_trav_launches = 2 * 6 * args.steps * max(1, -(-spp_step // max(1, min(16, (4 << 20) // max(1, W * H // world)))))
+        n_trav_launches = 7 * args.steps * max(1, -(-spp_step // (args.spp_per_wave or max(1, min(64, (16 << 20) // max(1, W * H // world))))))
         achieved = (rays / world) * a_ray / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
         line = {
             "metric": "path-tracing throughput", "value": round(value, 3), "unit": "Msamples/s", "n_gpus": world,
@@ -301,7 +306,7 @@ def main():
             "config": {"workload": args.workload, "scene": scene, "width": W, "height": H, "spp_total_config": total_spp,
                        "spp_per_step": spp_step, "parallelism": "row-tiles x%d" % world, "rng": "counter (seed 1234)",
                        "l2": "wavefront state per wave (~%d MB) exceeds L2 (%d MB); no explicit flush" %
-                             (176 * min((4 << 20), W * H * spp_step // world) >> 20, L2_BYTES >> 20)},
+                             (176 * min((16 << 20), W * H * spp_step // world) >> 20, L2_BYTES >> 20)},
             "clocks": clk.summary(),
             "e2e": {"value": round(e2e_value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes(fs),
                     "d2h_bytes_per_step": W * H * 4},

@@ -63,6 +63,7 @@ SYMBOLS = {
     "crt_resolve_f32": (C.c_int, [C.c_void_p, C.c_void_p]),
     "crt_read_accum": (C.c_int, [C.c_void_p, C.c_void_p]),
     "crt_reset": (C.c_int, [C.c_void_p]),
+    "crt_update_scene": (C.c_int, [C.c_void_p, C.POINTER(SceneDesc)]),
     "crt_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
     "crt_trace_closest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32]),
     "crt_trace_closest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]),

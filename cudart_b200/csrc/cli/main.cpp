@@ -20,6 +20,7 @@
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/crt_abi.h"
@@ -92,7 +93,16 @@ public:
     }
     void renderOneSamplePerPixel(uint8_t*) { render(1); }
     void render(unsigned spp) {                          // batch form: `spp` calls of renderOneSamplePerPixel
-        for (crt_ctx* c : ctx) CRT(crt_render(c, spp));  // asynchronous on each GPU's stream
+        // One host thread per GPU: a render is thousands of launches per device and the driver's launch queue is
+        // finite, so a single thread would feed the GPUs one after the other.
+        vector<thread> workers;
+        vector<string> errors(ctx.size());
+        for (size_t g = 0; g < ctx.size(); g++)
+            workers.emplace_back([&, g] {
+                if (crt_render(ctx[g], spp) != CRT_OK || crt_sync(ctx[g]) != CRT_OK) errors[g] = crt_last_error();
+            });
+        for (thread& t : workers) t.join();
+        for (const string& e : errors) if (!e.empty()) fatal("crt_render: " + e);
         samplesRendered += spp;
     }
     void copyImageBytes(uint8_t*) {                      // Renderer::copyImageBytes: gather, resolve, gamma

@@ -46,11 +46,16 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
-    cudaError_t alloc(size_t count) {
+    size_t cap = 0;
+    cudaError_t alloc(size_t count) {                 // keeps the allocation when it is already large enough
         n = count;
-        return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (p && count <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = std::max<size_t>(count, 1);
+        return cudaMalloc(&p, cap * sizeof(T));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
 }  // namespace
@@ -118,6 +123,94 @@ int check_kernel(const char* what) {
 
 }  // namespace
 
+// Validate, re-flatten and upload a scene into a context (crt_create and crt_update_scene).
+static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_t H) {
+    // ---- scene: re-flatten on the host, upload ----
+    const RefTriangle* tris = (const RefTriangle*)s->tris;
+    const RefNode* nodes = (const RefNode*)s->nodes;
+    for (uint32_t k = 0; k < s->n_nodes; k++) {
+        const RefNode& nd = nodes[k];
+        bool ok = nd.nTris > 0 ? ((uint32_t)nd.offset + (uint32_t)nd.nTris <= s->n_tris)
+                               : (nd.offset > (int32_t)k && (uint32_t)nd.offset < s->n_nodes && k + 1 < s->n_nodes);
+        if (!ok) return (fail(CRT_ERR_INVALID, "scene: BVH node %u is malformed", k));
+    }
+    for (uint32_t k = 0; k < s->n_lights; k++)
+        if (s->light_indices[k] >= s->n_tris) return (fail(CRT_ERR_INVALID, "scene: light index out of range"));
+    std::vector<WideNode> wide;
+    {
+        std::vector<RefNode> clustered;
+        if (!(c->flags & CRT_FLAG_REFERENCE_TOPOLOGY)) recluster_leaves(nodes, s->n_nodes, clustered);
+        c->wide_stats = clustered.empty() ? flatten_wide(nodes, s->n_nodes, tris, s->n_tris, wide)
+                                          : flatten_wide(clustered.data(), (uint32_t)clustered.size(), tris, s->n_tris, wide);
+    }
+    if (3 * c->wide_stats.depth + 4 > 64) return (fail(CRT_ERR_LIMIT, "scene: wide BVH depth %u exceeds the traversal stack", c->wide_stats.depth));
+    std::vector<TriIsect> isect;
+    std::vector<TriShade> shade;
+    make_tri_records(tris, s->n_tris, nodes, s->n_nodes, isect, shade);
+    for (uint32_t i = 0; i < s->n_tris; i++)
+        if (tris[i].materialId >= std::max(s->n_mats, 1u)) return (fail(CRT_ERR_INVALID, "scene: triangle %u has material %u of %u", i, tris[i].materialId, s->n_mats));
+    std::vector<float4> mats(4 * (size_t)std::max(s->n_mats, 1u));
+    for (uint32_t m = 0; m < s->n_mats; m++) {
+        const float* f = s->mat_floats + 12 * (size_t)m;
+        float bs, tx;
+        memcpy(&bs, &s->mat_indices[2 * m], 4);
+        memcpy(&tx, &s->mat_indices[2 * m + 1], 4);
+        if (s->mat_indices[2 * m + 1] >= (int32_t)s->n_tex) return (fail(CRT_ERR_INVALID, "scene: material %u texture index out of range", m));
+        mats[4 * m + 0] = make_float4(f[0], f[1], f[2], bs);
+        mats[4 * m + 1] = make_float4(f[3], f[4], f[5], tx);
+        mats[4 * m + 2] = make_float4(f[6], f[7], f[8], 0.f);
+        mats[4 * m + 3] = make_float4(f[9], f[10], f[11], 0.f);
+    }
+    int rc;
+#define UP(buf, src, count) if ((rc = upload(c->buf, src, count, c->stream)) != CRT_OK) return rc
+    UP(wide, wide.data(), wide.size() * 8);
+    UP(tri_isect, isect.data(), isect.size() * 3);
+    UP(tri_shade, shade.data(), shade.size() * 5);
+    UP(mats, mats.data(), mats.size());
+    UP(lights, s->light_indices, s->n_lights);
+    std::vector<float4> lboxes(2 * (size_t)s->n_lights);
+    {   // the reference leaf holding each light triangle
+        std::vector<uint32_t> leaf_of_first(s->n_tris, 0xffffffffu);
+        for (uint32_t j = 0; j < s->n_nodes; j++)
+            if (nodes[j].nTris > 0) leaf_of_first[(uint32_t)nodes[j].offset] = j;
+        for (uint32_t k = 0; k < s->n_lights; k++) {
+            const uint32_t j = leaf_of_first[isect[s->light_indices[k]].leafFirst];
+            if (j == 0xffffffffu) return (fail(CRT_ERR_INVALID, "scene: light %u is in no BVH leaf", k));
+            lboxes[2 * k] = make_float4(nodes[j].mn.x, nodes[j].mn.y, nodes[j].mn.z, 0.f);
+            lboxes[2 * k + 1] = make_float4(nodes[j].mx.x, nodes[j].mx.y, nodes[j].mx.z, 0.f);
+        }
+    }
+    UP(light_boxes, lboxes.data(), lboxes.size());
+    UP(tex_dims, s->tex_dims, 2 * (size_t)s->n_tex);
+    UP(tex_offsets, s->tex_offsets, s->n_tex ? s->n_tex + 1 : 0);
+    UP(tex_data, s->tex_data, 3 * (size_t)s->tex_texels);
+    uint8_t lut[256];
+    {   // gammaCorrectPixel (renderer.cu:495-504) tabulated with the host's powf, i.e. the reference's own libm
+        const float invGamma = 1.f / 2.2f;
+        for (int v = 0; v < 256; v++) lut[v] = (unsigned char)(powf((float)v * 1.f / 255.f, invGamma) * 255.f);
+    }
+    UP(gamma_lut, lut, 256);
+#undef UP
+    DScene& sc = c->sc;
+    sc.wide = c->wide.p; sc.tri_isect = c->tri_isect.p; sc.tri_shade = c->tri_shade.p; sc.mats = c->mats.p;
+    sc.lights = c->lights.p; sc.light_boxes = c->light_boxes.p; sc.tex_data = c->tex_data.p; sc.tex_dims = c->tex_dims.p; sc.tex_offsets = c->tex_offsets.p;
+    sc.n_wide = (uint32_t)wide.size(); sc.n_tris = s->n_tris; sc.n_mats = s->n_mats; sc.n_lights = s->n_lights;
+    sc.n_tex = s->n_tex; sc.tex_texels = s->tex_texels; sc.lights_area = s->lights_area;
+    memcpy(&sc.cam, s->camera, sizeof(RefCamera));
+    sc.cam.xpixels = (int32_t)W;
+    sc.cam.ypixels = (int32_t)H;
+    {
+        bool bounded = true;
+        for (uint32_t k = 0; k < s->n_nodes && bounded; k++) {
+            const float v[6] = {nodes[k].mn.x, nodes[k].mn.y, nodes[k].mn.z, nodes[k].mx.x, nodes[k].mx.y, nodes[k].mx.z};
+            for (float f : v) bounded = bounded && std::isfinite(f) && std::fabs(f) < 1e8f;
+        }
+        sc.coords_bounded = bounded ? 1 : 0;
+    }
+
+    return CRT_OK;
+}
+
 extern "C" {
 
 int crt_abi_version(void) { return CRT_ABI_VERSION; }
@@ -166,88 +259,7 @@ int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_option
     c->cfg.sms = prop.multiProcessorCount;
     c->cfg.stream = c->stream;
 
-    // ---- scene: re-flatten on the host, upload ----
-    const RefTriangle* tris = (const RefTriangle*)s->tris;
-    const RefNode* nodes = (const RefNode*)s->nodes;
-    for (uint32_t k = 0; k < s->n_nodes; k++) {
-        const RefNode& nd = nodes[k];
-        bool ok = nd.nTris > 0 ? ((uint32_t)nd.offset + (uint32_t)nd.nTris <= s->n_tris)
-                               : (nd.offset > (int32_t)k && (uint32_t)nd.offset < s->n_nodes && k + 1 < s->n_nodes);
-        if (!ok) return bail(fail(CRT_ERR_INVALID, "crt_create: BVH node %u is malformed", k));
-    }
-    for (uint32_t k = 0; k < s->n_lights; k++)
-        if (s->light_indices[k] >= s->n_tris) return bail(fail(CRT_ERR_INVALID, "crt_create: light index out of range"));
-    std::vector<WideNode> wide;
-    {
-        std::vector<RefNode> clustered;
-        if (!(o.flags & CRT_FLAG_REFERENCE_TOPOLOGY)) recluster_leaves(nodes, s->n_nodes, clustered);
-        c->wide_stats = clustered.empty() ? flatten_wide(nodes, s->n_nodes, tris, s->n_tris, wide)
-                                          : flatten_wide(clustered.data(), (uint32_t)clustered.size(), tris, s->n_tris, wide);
-    }
-    if (3 * c->wide_stats.depth + 4 > 64) return bail(fail(CRT_ERR_LIMIT, "crt_create: wide BVH depth %u exceeds the traversal stack", c->wide_stats.depth));
-    std::vector<TriIsect> isect;
-    std::vector<TriShade> shade;
-    make_tri_records(tris, s->n_tris, nodes, s->n_nodes, isect, shade);
-    for (uint32_t i = 0; i < s->n_tris; i++)
-        if (tris[i].materialId >= std::max(s->n_mats, 1u)) return bail(fail(CRT_ERR_INVALID, "crt_create: triangle %u has material %u of %u", i, tris[i].materialId, s->n_mats));
-    std::vector<float4> mats(4 * (size_t)std::max(s->n_mats, 1u));
-    for (uint32_t m = 0; m < s->n_mats; m++) {
-        const float* f = s->mat_floats + 12 * (size_t)m;
-        float bs, tx;
-        memcpy(&bs, &s->mat_indices[2 * m], 4);
-        memcpy(&tx, &s->mat_indices[2 * m + 1], 4);
-        if (s->mat_indices[2 * m + 1] >= (int32_t)s->n_tex) return bail(fail(CRT_ERR_INVALID, "crt_create: material %u texture index out of range", m));
-        mats[4 * m + 0] = make_float4(f[0], f[1], f[2], bs);
-        mats[4 * m + 1] = make_float4(f[3], f[4], f[5], tx);
-        mats[4 * m + 2] = make_float4(f[6], f[7], f[8], 0.f);
-        mats[4 * m + 3] = make_float4(f[9], f[10], f[11], 0.f);
-    }
-    int rc;
-#define UP(buf, src, count) if ((rc = upload(c->buf, src, count, c->stream)) != CRT_OK) return bail(rc)
-    UP(wide, wide.data(), wide.size() * 8);
-    UP(tri_isect, isect.data(), isect.size() * 3);
-    UP(tri_shade, shade.data(), shade.size() * 5);
-    UP(mats, mats.data(), mats.size());
-    UP(lights, s->light_indices, s->n_lights);
-    std::vector<float4> lboxes(2 * (size_t)s->n_lights);
-    {   // the reference leaf holding each light triangle
-        std::vector<uint32_t> leaf_of_first(s->n_tris, 0xffffffffu);
-        for (uint32_t j = 0; j < s->n_nodes; j++)
-            if (nodes[j].nTris > 0) leaf_of_first[(uint32_t)nodes[j].offset] = j;
-        for (uint32_t k = 0; k < s->n_lights; k++) {
-            const uint32_t j = leaf_of_first[isect[s->light_indices[k]].leafFirst];
-            if (j == 0xffffffffu) return bail(fail(CRT_ERR_INVALID, "crt_create: light %u is in no BVH leaf", k));
-            lboxes[2 * k] = make_float4(nodes[j].mn.x, nodes[j].mn.y, nodes[j].mn.z, 0.f);
-            lboxes[2 * k + 1] = make_float4(nodes[j].mx.x, nodes[j].mx.y, nodes[j].mx.z, 0.f);
-        }
-    }
-    UP(light_boxes, lboxes.data(), lboxes.size());
-    UP(tex_dims, s->tex_dims, 2 * (size_t)s->n_tex);
-    UP(tex_offsets, s->tex_offsets, s->n_tex ? s->n_tex + 1 : 0);
-    UP(tex_data, s->tex_data, 3 * (size_t)s->tex_texels);
-    uint8_t lut[256];
-    {   // gammaCorrectPixel (renderer.cu:495-504) tabulated with the host's powf, i.e. the reference's own libm
-        const float invGamma = 1.f / 2.2f;
-        for (int v = 0; v < 256; v++) lut[v] = (unsigned char)(powf((float)v * 1.f / 255.f, invGamma) * 255.f);
-    }
-    UP(gamma_lut, lut, 256);
-#undef UP
-    DScene& sc = c->sc;
-    sc.wide = c->wide.p; sc.tri_isect = c->tri_isect.p; sc.tri_shade = c->tri_shade.p; sc.mats = c->mats.p;
-    sc.lights = c->lights.p; sc.light_boxes = c->light_boxes.p; sc.tex_data = c->tex_data.p; sc.tex_dims = c->tex_dims.p; sc.tex_offsets = c->tex_offsets.p;
-    sc.n_wide = (uint32_t)wide.size(); sc.n_tris = s->n_tris; sc.n_mats = s->n_mats; sc.n_lights = s->n_lights;
-    sc.n_tex = s->n_tex; sc.tex_texels = s->tex_texels; sc.lights_area = s->lights_area;
-    memcpy(&sc.cam, s->camera, sizeof(RefCamera));
-    sc.cam.xpixels = (int32_t)W;
-    sc.cam.ypixels = (int32_t)H;
-    {
-        bool bounded = true;
-        for (uint32_t k = 0; k < s->n_nodes && bounded; k++) {
-            const float v[6] = {nodes[k].mn.x, nodes[k].mn.y, nodes[k].mn.z, nodes[k].mx.x, nodes[k].mx.y, nodes[k].mx.z};
-            for (float f : v) bounded = bounded && std::isfinite(f) && std::fabs(f) < 1e8f;
-        }
-        sc.coords_bounded = bounded ? 1 : 0;
-    }
+    { const int rc_scene = upload_scene(c, s, W, H); if (rc_scene != CRT_OK) return bail(rc_scene); }
 
     // ---- pixel ownership ----
     DTiling& tl = c->tl;
@@ -261,9 +273,14 @@ int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_option
 
     // ---- wave buffers ----
     uint32_t k = o.spp_per_wave;
-    if (k == 0) {       // auto: about 4M paths in flight, at least 1 spp
-        k = (uint32_t)std::max<uint64_t>(1, (4ull << 20) / std::max<uint32_t>(tl.local_pixels, 1));
-        k = std::min<uint32_t>(k, 16);
+    if (k == 0) {       // auto: about 16M paths in flight (~3 GB of wave state; measured +12 % over 4M), within a
+                        // quarter of the free device memory, at least 1 spp
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const uint64_t by_mem = std::max<uint64_t>(1u << 20, free_b / 4 / 192);
+        const uint64_t target = std::min<uint64_t>(16ull << 20, by_mem);
+        k = (uint32_t)std::max<uint64_t>(1, target / std::max<uint32_t>(tl.local_pixels, 1));
+        k = std::min<uint32_t>(k, 64);
     }
     c->spp_per_wave = k;
     const size_t cap = std::max<size_t>((size_t)tl.local_pixels * k, 32);
@@ -320,17 +337,18 @@ int crt_render(crt_ctx* c, uint32_t spp) {
         mark(-1);
         launch_raygen(c->sc, c->tl, c->wv, c->samples + done, k, c->seed, c->cfg);
         mark(CRT_STAGE_RAYGEN);
+        // traverse(E0); shade(0); traverse(E1 + S0); shade(1); ... traverse(E5 + S4); shade(5); traverse(S5)
         for (int bounce = 0; bounce < kMaxBounces; bounce++) {
-            launch_extend(c->sc, c->wv, bounce, exact, stats, c->cfg);
+            launch_traverse(c->sc, c->wv, bounce, bounce - 1, exact, stats, c->cfg);
             mark(CRT_STAGE_EXTEND);
             launch_shade(c->sc, c->tl, c->wv, bounce, c->cfg);
             mark(CRT_STAGE_SHADE);
-            launch_shadow(c->sc, c->wv, bounce, exact, stats, c->cfg);
-            mark(CRT_STAGE_SHADOW);
         }
+        launch_traverse(c->sc, c->wv, -1, kMaxBounces - 1, exact, stats, c->cfg);
+        mark(CRT_STAGE_SHADOW);
         launch_accumulate(c->tl, c->wv, c->accum.p, k, c->cfg);
         mark(CRT_STAGE_ACCUM);
-        c->launches += 2 + 3 * kMaxBounces;
+        c->launches += 3 + 2 * kMaxBounces;
         done += k;
     }
     CU(cudaEventRecord(b, c->stream));
@@ -399,6 +417,19 @@ int crt_read_accum(crt_ctx* c, float* dst) {
 int crt_resolve_gathered(crt_ctx* c, const void* d_gathered, uint8_t* rgba8_dst, float* f32_dst) {
     if (!c || !d_gathered) return fail(CRT_ERR_INVALID, "crt_resolve_gathered: null argument");
     return resolve_common(c, (const float4*)d_gathered, true, rgba8_dst, f32_dst, 1);
+}
+
+int crt_update_scene(crt_ctx* c, const crt_scene_desc* s) {
+    if (!c || !s) return fail(CRT_ERR_INVALID, "crt_update_scene: null argument");
+    if (!s->tris || !s->nodes || !s->n_tris || !s->n_nodes || !s->camera) return fail(CRT_ERR_INVALID, "crt_update_scene: empty scene");
+    if (s->n_mats > 128) return fail(CRT_ERR_LIMIT, "crt_update_scene: %u materials > MAX_MATERIALS 128", s->n_mats);
+    if (s->n_tris >= kMaxTris) return fail(CRT_ERR_LIMIT, "crt_update_scene: %u triangles >= %u", s->n_tris, kMaxTris);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));                    // the previous frame may still be reading the old arrays
+    int rc = upload_scene(c, s, c->tl.W, c->tl.H);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));                    // host staging vectors die with this call
+    return crt_reset(c);
 }
 
 int crt_reset(crt_ctx* c) {

@@ -68,9 +68,9 @@ struct LaunchCfg { int sms; cudaStream_t stream; };
 
 void launch_raygen(const DScene& sc, const DTiling& tl, const DWave& wv, uint32_t first_sample, uint32_t wave_spp,
                    uint32_t seed, const LaunchCfg& cfg);
-void launch_extend(const DScene& sc, const DWave& wv, int bounce, bool exact, bool stats, const LaunchCfg& cfg);
+// One persistent traversal launch for the extend queue of `ebounce` and the shadow queue of `sbounce` (-1: none).
+void launch_traverse(const DScene& sc, const DWave& wv, int ebounce, int sbounce, bool exact, bool stats, const LaunchCfg& cfg);
 void launch_shade(const DScene& sc, const DTiling& tl, const DWave& wv, int bounce, const LaunchCfg& cfg);
-void launch_shadow(const DScene& sc, const DWave& wv, int bounce, bool exact, bool stats, const LaunchCfg& cfg);
 void launch_accumulate(const DTiling& tl, const DWave& wv, float4* accum, uint32_t wave_spp, const LaunchCfg& cfg);
 // Stand-alone closest-hit over a flat ray array (crt_trace_closest): rays as 8 floats, hits as (t,u,v,tri).
 void launch_trace(const DScene& sc, const float4* rays, uint32_t n, float4* hits, uint32_t* head, DStats* stats,

@@ -85,6 +85,11 @@ class B200Renderer:
     def reset(self) -> None:
         capi.check(self._lib.crt_reset(self._h))
 
+    def update_scene(self, scene: FlatScene) -> None:
+        """Upload another scene (same image size) into the live renderer and start a fresh accumulation."""
+        desc, self._keep = scene_desc(scene)
+        capi.check(self._lib.crt_update_scene(self._h, C.byref(desc)))
+
     def image_f32(self) -> np.ndarray:
         out = np.empty((self.height, self.width, 3), np.float32)
         capi.check(self._lib.crt_resolve_f32(self._h, out.ctypes.data))

@@ -112,6 +112,9 @@ int crt_resolve_f32(crt_ctx* ctx, float* dst);
 /* Raw radiance SUMS, W*H*3 floats (what SequentialRenderer keeps in h_imgVectorPtr). */
 int crt_read_accum(crt_ctx* ctx, float* dst);
 int crt_reset(crt_ctx* ctx);                                  /* zero accumulator and sample count */
+/* Replace the scene of a live context (next frame of an animation: new geometry / camera / materials), keeping the
+ * image size, sharding and all device buffers; copies host -> device like crt_create and resets the accumulator. */
+int crt_update_scene(crt_ctx* ctx, const crt_scene_desc* scene);
 int crt_get_counters(crt_ctx* ctx, crt_counters* out);
 
 /* ---- bit-exact test entry: closest hit of the reference traversal (renderer.cu:283-330) -------- */

@@ -313,3 +313,22 @@ def test_command_line_end_to_end_writes_the_same_png(tmp_path, B200Renderer):
     import json
     m = json.load(open(tmp_path / "m.json"))
     assert m["spp"] == 8 and m["msamples_per_s"] > 0 and m["kernel_launches"] > 0
+
+
+def test_update_scene_equals_a_fresh_renderer(golden, B200Renderer):
+    """crt_update_scene re-uploads host arrays into a live context (buffers reused or regrown) and restarts accumulation."""
+    small, _ = golden("cornell")
+    big, _ = golden("monkeys")
+    W, H = 64, 48
+    r = B200Renderer(small.with_resolution(W, H), W, H, 4)
+    r.render(3)
+    for fs in (big, small):
+        fs = fs.with_resolution(W, H)
+        r.update_scene(fs)
+        assert r.getSamplesRendered() == 0
+        r.render(4)
+        fresh = B200Renderer(fs, W, H, 4)
+        fresh.render(4)
+        assert np.array_equal(r.accum(), fresh.accum())
+        fresh.close()
+    r.close()
