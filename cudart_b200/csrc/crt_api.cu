@@ -134,6 +134,9 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
                                : (nd.offset > (int32_t)k && (uint32_t)nd.offset < s->n_nodes && k + 1 < s->n_nodes);
         if (!ok) return (fail(CRT_ERR_INVALID, "scene: BVH node %u is malformed", k));
     }
+    if (s->n_lights == 0 || !s->light_indices || !(s->lights_area > 0.f))
+        return fail(CRT_ERR_INVALID, "scene: no emissive triangles (the reference divides by a zero light area and indexes an empty "
+                                     "light list in that case, SURVEY.md D13)");
     for (uint32_t k = 0; k < s->n_lights; k++)
         if (s->light_indices[k] >= s->n_tris) return (fail(CRT_ERR_INVALID, "scene: light index out of range"));
     std::vector<WideNode> wide;

@@ -265,6 +265,9 @@ def test_errors_are_codes_not_crashes(golden, B200Renderer):
     bad = dataclasses.replace(fs, light_indices=np.array([10 ** 6], np.uint32))
     with pytest.raises(capi.CrtError):
         B200Renderer(bad, 16, 16)
+    dark = dataclasses.replace(fs, light_indices=np.zeros(0, np.uint32), lights_area=0.0)
+    with pytest.raises(capi.CrtError, match="no emissive"):
+        B200Renderer(dark, 16, 16)
 
 
 def _read_png_rgba(path):
