@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--workload", default="cornellSphere_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--spp-per-step", type=int, default=SPP_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-smem-nodes", action="store_true", help="A/B: never stage BVH nodes in shared memory")
     ap.add_argument("--spp-per-wave", type=int, default=0, help="samples per pixel per wavefront batch (0 = auto, ~4M paths)")
     args = ap.parse_args()
     scene, W, H, total_spp = WORKLOADS[args.workload]
@@ -226,7 +227,7 @@ def main():
     spp_step = args.spp_per_step * world                      # weak scaling: per-GPU work fixed
     stream = torch.cuda.current_stream().cuda_stream
     r = B200Renderer(fs, W, H, total_spp, device=local, rank=rank, world=world, profile=True, stream=stream,
-                     spp_per_wave=args.spp_per_wave)
+                     spp_per_wave=args.spp_per_wave, smem_nodes=False if args.no_smem_nodes else None)
 
     def barrier():
         if world > 1:

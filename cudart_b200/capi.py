@@ -7,12 +7,14 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcrt_b200.so")
+LIB_PATH = os.environ.get("CRT_LIB") or os.path.join(_HERE, "libcrt_b200.so")   # CRT_LIB: tuning builds only
 
 CRT_FLAG_EXACT_VISIT = 1
 CRT_FLAG_PROFILE = 2
 CRT_FLAG_STATS = 4
 CRT_FLAG_REFERENCE_TOPOLOGY = 8
+CRT_FLAG_NO_SMEM_NODES = 16
+CRT_FLAG_SMEM_TOP_LEVELS = 32
 CRT_MISS = 0xFFFFFFFF
 STAGES = ("raygen", "extend", "shade", "shadow", "accumulate")
 

@@ -387,9 +387,10 @@ WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, const RefTriangle
 
     uint32_t root = new_wide();
     todo.push_back({0, root, 1});
-    while (!todo.empty()) {
-        Item it = todo.back();
-        todo.pop_back();
+    // breadth-first: wide-node indices grow level by level, so "the first M nodes" are the top of the tree
+    // (that prefix is what the traversal kernels stage in shared memory)
+    for (size_t head = 0; head < todo.size(); head++) {
+        Item it = todo[head];
         st.depth = std::max(st.depth, it.depth);
         std::vector<Slot> slots;
         const RefNode& top = nodes[it.bin];

@@ -19,6 +19,7 @@ struct DScene {
     const uint32_t* tex_dims;
     const uint32_t* tex_offsets;
     uint32_t n_wide, n_tris, n_mats, n_lights, n_tex, tex_texels;
+    uint32_t n_smem_nodes;     // the first n_smem_nodes wide nodes (top levels, breadth-first) are staged in shared memory
     float lights_area;
     int coords_bounded;        // every node/triangle coordinate is finite and below 1e8 in magnitude
     RefCamera cam;
@@ -65,6 +66,9 @@ struct DWave {
 };
 
 struct LaunchCfg { int sms; cudaStream_t stream; };
+
+constexpr uint32_t kMaxSmemNodes = 288;        // 36 KB of nodes + 20 KB of stack per CTA, 4 CTAs per SM: 224 of 227 KB
+int configure_kernels();                       // opt the traversal kernels into > 48 KB of dynamic shared memory
 
 void launch_raygen(const DScene& sc, const DTiling& tl, const DWave& wv, uint32_t first_sample, uint32_t wave_spp,
                    uint32_t seed, const LaunchCfg& cfg);

@@ -71,6 +71,8 @@ typedef struct crt_options {
 #define CRT_FLAG_EXACT_VISIT 1u  /* no distance culling: visit exactly the leaves the reference visits     */
 #define CRT_FLAG_PROFILE 2u      /* time every stage with CUDA events (crt_get_counters.stage_ms)          */
 #define CRT_FLAG_REFERENCE_TOPOLOGY 8u /* keep the reference's interior BVH structure (no SAH re-clustering of its leaves) */
+#define CRT_FLAG_NO_SMEM_NODES 16u /* never stage BVH nodes in shared memory (default: staged when the whole wide tree fits) */
+#define CRT_FLAG_SMEM_TOP_LEVELS 32u /* stage the top levels even when the tree does not fit entirely (A/B measurements) */
 #define CRT_FLAG_STATS 4u        /* count wide-node fetches and triangle tests (slows traversal a little)  */
 
 typedef struct crt_ray { float ox, oy, oz, dx, dy, dz, tmin, tmax; } crt_ray;   /* == reference Ray       */

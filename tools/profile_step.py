@@ -14,7 +14,7 @@ spp = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 waves = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 scene, W, H, _ = WORKLOADS[wl]
 r = B200Renderer(load_scene(scene, W, H), W, H, spp, spp_per_wave=spp, stats=bool(os.environ.get("CRT_STATS")),
-                 reference_topology=bool(os.environ.get("CRT_REFTOPO")), exact_visit=bool(os.environ.get("CRT_EXACT")))
+                 reference_topology=bool(os.environ.get("CRT_REFTOPO")), exact_visit=bool(os.environ.get("CRT_EXACT")), smem_nodes=False if os.environ.get("CRT_NOSMEM") else (True if os.environ.get("CRT_SMEMTOP") else None))
 for _ in range(waves):
     r.render(spp)
 r.sync()
