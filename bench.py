@@ -299,6 +299,13 @@ def main():
         a_ray, od = algorithmic_bytes(scene, W, H)
         n_trav_launches = 7 * args.steps * max(1, -(-spp_step // (args.spp_per_wave or max(1, min(64, (16 << 20) // max(1, W * H // world))))))
         achieved = (rays / world) * a_ray / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
+        traffic, physical = None, None
+        try:            # ncu DRAM bytes per traversal launch for this workload (profiles/, captured with the same wave size)
+            t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
+            if t and (args.spp_per_wave in (0, t["spp_per_wave"])) and world == 1:
+                traffic, physical = t["dram_bytes_per_launch"], t["ncu"]
+        except (OSError, ValueError):
+            pass
         line = {
             "metric": "path-tracing throughput", "value": round(value, 3), "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
@@ -315,7 +322,10 @@ def main():
             "stage_ms": stage,
             "roofline": {"bound": "hbm", "kernel": "k_extend+k_shadow (BVH traversal)", "achieved": round(achieved, 2) if achieved else None,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
-                         "traffic": None, "bytes_per_ray": round(a_ray, 1), "launches": n_trav_launches,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": round((rays / world) * a_ray / max(n_trav_launches, 1), 0),
+                         "bytes_per_ray": round(a_ray, 1), "launches": n_trav_launches, "physical_limiter_ncu": physical,
+                         "note": "algorithmic bytes follow the REFERENCE traversal (no distance culling, SURVEY.md 8(d)); the scene is "
+                                 "cache resident and this path culls, so frac can exceed 1 - ncu shows the kernel is issue-bound, not HBM-bound",
                          "reference_traversal": {k: round(od[k], 3) for k in ("rays_per_sample", "nodes_per_ray", "tris_per_ray")}},
         }
         if world == 1 and not args.no_cpu_baseline:

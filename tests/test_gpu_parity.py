@@ -345,3 +345,25 @@ def test_update_scene_equals_a_fresh_renderer(golden, B200Renderer):
         assert np.array_equal(r.accum(), fresh.accum())
         fresh.close()
     r.close()
+
+
+def test_degenerate_image_shapes_and_empty_ranks(golden, B200Renderer):
+    """1x1 and odd-sized images, fewer row tiles than ranks (ranks that own nothing), zero samples."""
+    fs, _ = golden("cornell")
+    for (W, H) in ((1, 1), (33, 7), (5, 17)):
+        s = fs.with_resolution(W, H)
+        want, _ = orc.OracleScene(s).render_accum(4, rng=orc.RNG_COUNTER, seed=3)
+        full = B200Renderer(s, W, H, 4, seed=3)
+        full.render(0)
+        assert full.getSamplesRendered() == 0 and not full.accum().any()
+        full.render(4)
+        got = full.accum()
+        assert np.isfinite(got).all() and abs(float(got.sum()) / float(want.sum()) - 1) < 0.02
+        parts = np.zeros_like(got)
+        for k in range(4):                                  # H=7 -> one tile: ranks 1..3 own no rows
+            p = B200Renderer(s, W, H, 4, seed=3, rank=k, world=4)
+            p.render(4)
+            parts += p.accum()
+            p.close()
+        assert np.array_equal(parts, got)
+        full.close()
