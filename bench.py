@@ -209,6 +209,15 @@ def main():
     scene, W, H, total_spp = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, scene, W, H, total_spp)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: `python bench.py --gpus N` re-launches itself the way the driver does (one rank per GPU)
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                                   "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
 
     import torch
     import torch.distributed as dist
