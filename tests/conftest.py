@@ -9,7 +9,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-SCENES = ["cornell", "cornellSphere", "monkeys", "terrain64"]
+SCENES = ["cornell", "cornellSphere", "monkeys", "terrain64", "tiny"]
 
 
 def pytest_configure(config):

@@ -43,14 +43,16 @@ REF_DUMP = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 #        scene          W   H  spp
-SCENES = [("cornell", 64, 48, 4), ("cornellSphere", 64, 48, 4), ("monkeys", 64, 48, 4), ("terrain64", 48, 32, 2)]
+SCENES = [("cornell", 64, 48, 4), ("cornellSphere", 64, 48, 4), ("monkeys", 64, 48, 4), ("terrain64", 48, 32, 2),
+          ("tiny", 40, 30, 4)]          # tests/golden/tiny: hand-written loader corner cases, DOF camera, every BSDF
 N_HARVEST, N_RANDOM, N_SPECIAL = 6000, 3000, 3000
 HI_W, HI_H, HI_SPP = 32, 24, 256
 
 
 def ref_dump(scene, W, H, *extra):
-    cmd = [REF_DUMP, "--obj", f"{ASSETS}/meshes/{scene}.obj", "--camera", f"{ASSETS}/settings/{scene}-camera.json",
-           "--textures", f"{ASSETS}/textures/", "-w", str(W), "-h", str(H), *extra]
+    assets = os.path.join(OUT, "tiny") if scene == "tiny" else ASSETS
+    cmd = [REF_DUMP, "--obj", f"{assets}/meshes/{scene}.obj", "--camera", f"{assets}/settings/{scene}-camera.json",
+           "--textures", f"{assets}/textures/", "-w", str(W), "-h", str(H), *extra]
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
 
 
