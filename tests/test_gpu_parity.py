@@ -367,3 +367,24 @@ def test_degenerate_image_shapes_and_empty_ranks(golden, B200Renderer):
             p.close()
         assert np.array_equal(parts, got)
         full.close()
+
+
+def test_command_line_shards_over_two_gpus_identically(tmp_path):
+    """`./CudaRT --gpus 2`: one context per GPU in one process, one NCCL all-gather, same PNG as one GPU."""
+    import os
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tiny = os.path.join(root, "tests", "golden", "tiny")
+    (tmp_path / ".env").write_text("MESHES_PATH=%s/meshes\nCAMERA_PATH=%s/settings\nTEXTURES_PATH=%s/textures\n" % (tiny, tiny, tiny))
+    images = []
+    for gpus in (1, 2):
+        wd = tmp_path / ("build%d" % gpus)
+        wd.mkdir()
+        p = subprocess.run([os.path.join(root, "cudart_b200", "CudaRT"), "-f", "tiny", "-s", "16", "-w", "70", "-h", "45",
+                            "--gpus", str(gpus)], cwd=wd, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        images.append(_read_png_rgba(wd / "tiny.png"))
+    assert np.array_equal(images[0], images[1])
