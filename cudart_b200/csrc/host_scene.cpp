@@ -456,6 +456,24 @@ WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, const RefTriangle
             }
         }
     }
+    // One cull bound per wide node (the loosest of its children), replicated in the four aux words: the kernel decodes
+    // it once per node instead of once per child.
+    for (WideNode& w : out) {
+        float A = 1.f, B = 0.f;
+        bool any = false;
+        for (int c = 0; c < 4; c++) {
+            if (w.child[c] == kEmptyChild) continue;
+            uint32_t a = w.aux[c] & 0xffff0000u, b = w.aux[c] << 16;
+            float fa, fb;
+            std::memcpy(&fa, &a, 4);
+            std::memcpy(&fb, &b, 4);
+            A = any ? std::min(A, fa) : fa;
+            B = any ? std::max(B, fb) : fb;
+            any = true;
+        }
+        const uint32_t packed = pack_cull_bound({any ? A : 0.f, any ? B : INFINITY});
+        for (int c = 0; c < 4; c++) w.aux[c] = packed;
+    }
     st.n_wide = (uint32_t)out.size();
     return st;
 }

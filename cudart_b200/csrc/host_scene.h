@@ -43,7 +43,8 @@ static_assert(sizeof(RefCamera) == 72, "reference Camera layout");
 struct WideNode {
     float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
     int32_t child[4];         // >= 0: index of a WideNode; < 0: leaf, see leaf_ref(); kEmptyChild: unused slot
-    uint32_t aux[4];          // per child: packed CullBound of the subtree (pack_cull_bound)
+    uint32_t aux[4];          // packed CullBound (pack_cull_bound) of the node = loosest of its children's subtrees,
+                              // replicated in all four words (the kernel decodes word 0)
 };
 static_assert(sizeof(WideNode) == 128, "wide node is one 128-byte line");
 
