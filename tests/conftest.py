@@ -9,7 +9,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-SCENES = ["cornell", "cornellSphere", "monkeys", "terrain64", "tiny"]
+SCENES = ["cornell", "cornellSphere", "monkeys", "terrain64", "tiny", "soup"]
 
 
 def pytest_configure(config):

@@ -44,13 +44,14 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 
 #        scene          W   H  spp
 SCENES = [("cornell", 64, 48, 4), ("cornellSphere", 64, 48, 4), ("monkeys", 64, 48, 4), ("terrain64", 48, 32, 2),
-          ("tiny", 40, 30, 4)]          # tests/golden/tiny: hand-written loader corner cases, DOF camera, every BSDF
+          ("tiny", 40, 30, 4),          # tests/golden/tiny: hand-written loader corner cases, DOF camera, every BSDF
+          ("soup", 48, 36, 4)]          # tests/golden/soup: oversized leaf, duplicate triangles, slivers, random soup
 N_HARVEST, N_RANDOM, N_SPECIAL = 6000, 3000, 3000
 HI_W, HI_H, HI_SPP = 32, 24, 256
 
 
 def ref_dump(scene, W, H, *extra):
-    assets = os.path.join(OUT, "tiny") if scene == "tiny" else ASSETS
+    assets = os.path.join(OUT, scene) if scene in ("tiny", "soup") else ASSETS
     cmd = [REF_DUMP, "--obj", f"{assets}/meshes/{scene}.obj", "--camera", f"{assets}/settings/{scene}-camera.json",
            "--textures", f"{assets}/textures/", "-w", str(W), "-h", str(H), *extra]
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)

@@ -60,9 +60,17 @@ def test_wide_flattening_covers_every_reference_leaf_once(golden, name):
                 seen[(first, cnt)] = (lo[n, :, c], hi[n, :, c])
             else:
                 interior.append(ref)
-    assert set(seen) == set(want)                       # fixture leaves all hold <= 32 triangles
-    for k, (mn, mx) in seen.items():                    # leaf boxes are the reference's, bit for bit
-        assert np.array_equal(mn, want[k][0]) and np.array_equal(mx, want[k][1])
+    # every reference leaf is covered exactly once, by one reference (<= 32 triangles) or by consecutive chunks
+    # (the 40-triangle leaf of `soup`), and every chunk carries the reference leaf's own box, bit for bit
+    starts = sorted(want)
+    covered = {k: 0 for k in want}
+    for (first, cnt), (mn, mx) in sorted(seen.items()):
+        owner = max(k for k in starts if k[0] <= first)
+        assert first + cnt <= owner[0] + owner[1] and cnt <= 32
+        assert first == owner[0] + covered[owner], "chunks must tile the leaf in order"
+        covered[owner] += cnt
+        assert np.array_equal(mn, want[owner][0]) and np.array_equal(mx, want[owner][1])
+    assert all(covered[k] == k[1] for k in want)
     assert sorted(interior) == list(range(1, wide.shape[0]))   # every wide node but the root has one parent
 
 
