@@ -1,6 +1,7 @@
 // cudart_b200/csrc/cli/main.cpp - `CudaRT`: the reference's command line on top of the B200 path.
 //
-//   ./CudaRT -f <scene> -s <spp> -w <width> -h <height> [--cpu] [--gpus N] [--dump-scene F] [--no-render] [--metrics F]
+//   ./CudaRT -f <scene> -s <spp> -w <width> -h <height> [--cpu] [--gpus N] [--progress N] [--dump-scene F] [--no-render]
+//            [--metrics F]
 //
 // Same flags, defaults, `../.env` lookup with the `../meshes|settings|textures` fallback, same progress lines and
 // the same three closing lines as the reference's main (main.cpp:24-188); output goes to <scene>.png in the
@@ -152,9 +153,25 @@ private:
 
 // TerminalLauncher::render (terminal_launcher.cpp:10-16), batched: the renderer is told how many samples follow
 // so that it can trace them in large wavefront batches instead of one launch sequence per sample.
-void launch(B200Renderer& r) {
+void launch(B200Renderer& r, unsigned progress_every, const string& outFile) {
     uint8_t* img = r.getImgBytesPointer();
-    r.render((unsigned)r.getSamples());
+    if (progress_every == 0) {
+        r.render((unsigned)r.getSamples());
+    } else {
+        // headless stand-in for the reference's --x window (window.cpp:17-68): the running image is written to the
+        // output file every `progress_every` samples
+        for (unsigned done = 0, total = (unsigned)r.getSamples(); done < total;) {
+            const unsigned n = min(progress_every, total - done);
+            r.render(n);
+            done += n;
+            if (done < total) {
+                r.copyImageBytes(img);
+                write_png_rgba8(outFile, r.h_img.data(), r.getWidth(), r.getHeight());
+                cout << "\r" << done << " / " << total << " samples per pixel" << flush;
+            }
+        }
+        cout << endl;
+    }
     r.copyImageBytes(img);
 }
 
@@ -170,7 +187,7 @@ string self_dir() {
 }  // namespace
 
 int main(int argc, char* argv[]) {
-    int samples = 10, width = 640, height = 480, gpus = 1;
+    int samples = 10, width = 640, height = 480, gpus = 1, progress = 0;
     string outFile = "out.png", sceneName = "cornell";
     string objDir, cameraDir, texturePath, dumpScene, metricsFile;
     const string envPath = "../.env";
@@ -196,7 +213,8 @@ int main(int argc, char* argv[]) {
                 "-h \t<height>\tdefault:320px\n"
                 "-f \t<scene>\tdefault: cornell\n"
                 "--cpu \t<flag to run sequential code on CPU only>\tdefault: false\n"
-                "--gpus \t<number of B200s to shard the image over>\tdefault: 1\n";
+                "--gpus \t<number of B200s to shard the image over>\tdefault: 1\n"
+                "--progress \t<write the running image every N samples>\tdefault: off\n";
         return 1;
     }
     vector<string> args(argv + 1, argv + argc);
@@ -210,6 +228,7 @@ int main(int argc, char* argv[]) {
     value_of("-w", "-w", width);
     value_of("-h", "-h", height);
     value_of("--gpus", "--gpus", gpus);
+    value_of("--progress", "--progress", progress);
     if (find(args.begin(), args.end(), "--cpu") < args.end()) executeOnCpu = true;
     if (find(args.begin(), args.end(), "--no-render") < args.end()) noRender = true;
     auto str_of = [&](const char* flag, string& dst) {
@@ -265,7 +284,7 @@ int main(int argc, char* argv[]) {
 
     B200Renderer renderer(scene, (unsigned)width, (unsigned)height, (unsigned)samples, gpus);
     auto start = high_resolution_clock::now();
-    launch(renderer);
+    launch(renderer, (unsigned)max(progress, 0), outFile);
     auto stop = high_resolution_clock::now();
     write_png_rgba8(outFile, renderer.h_img.data(), (unsigned)width, (unsigned)height);     // Launcher::saveToImage
 
