@@ -326,7 +326,9 @@ def main():
                              (176 * min((16 << 20), W * H * spp_step // world) >> 20, L2_BYTES >> 20)},
             "clocks": clk.summary(),
             "e2e": {"value": round(e2e_value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes(fs),
-                    "d2h_bytes_per_step": W * H * 4},
+                    "d2h_bytes_per_step": W * H * 4,
+                    "note": "per step: crt_update_scene (host arrays -> re-flattened on the host -> device), crt_render, "
+                            "crt_resolve_rgba8 into host memory; host buffers are pageable numpy arrays"},
             "gpu_launches": int(launches),
             "stage_ms": stage,
             "roofline": {"bound": "hbm", "kernel": "k_extend+k_shadow (BVH traversal)", "achieved": round(achieved, 2) if achieved else None,
