@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--spp-per-step", type=int, default=SPP_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-smem-nodes", action="store_true", help="A/B: never stage BVH nodes in shared memory")
+    ap.add_argument("--tight-bvh", default="auto", choices=["auto", "on", "off"], help="A/B: per-triangle tight BVH (DESIGN.md 2.4)")
+    ap.add_argument("--stats", action="store_true", help="count node visits / triangle tests (slower; not a bench value)")
     ap.add_argument("--spp-per-wave", type=int, default=0, help="samples per pixel per wavefront batch (0 = auto, ~4M paths)")
     args = ap.parse_args()
     scene, W, H, total_spp = WORKLOADS[args.workload]
@@ -236,7 +238,8 @@ def main():
     spp_step = args.spp_per_step * world                      # weak scaling: per-GPU work fixed
     stream = torch.cuda.current_stream().cuda_stream
     r = B200Renderer(fs, W, H, total_spp, device=local, rank=rank, world=world, profile=True, stream=stream,
-                     spp_per_wave=args.spp_per_wave, smem_nodes=False if args.no_smem_nodes else None)
+                     spp_per_wave=args.spp_per_wave, smem_nodes=False if args.no_smem_nodes else None,
+                     tight_bvh={"auto": None, "on": True, "off": False}[args.tight_bvh], stats=args.stats)
 
     def barrier():
         if world > 1:
@@ -275,11 +278,17 @@ def main():
     value = samples / (ms * 1e-3) / 1e6
     launches = c1["kernel_launches"] - c0["kernel_launches"]
     stage = {k: round(c1["stage_ms"][k] - c0["stage_ms"][k], 3) for k in c1["stage_ms"]}
+    tight_nodes, tight_always = r.tight_info()
+    per_ray = None
+    if args.stats and rays > 0 and world == 1:
+        per_ray = {"wide_nodes_per_ray": round((c1["node_visits"] - c0["node_visits"]) / rays, 2),
+                   "tri_tests_per_ray": round((c1["tri_tests"] - c0["tri_tests"]) / rays, 2)}
     r.close()
 
     # ---- e2e through the public API with HOST buffers: every step uploads the scene (host -> device), renders
     # spp_step samples per pixel and reads the RGBA8 frame back (device -> host), like one frame of an animation ----
-    rr = B200Renderer(fs, W, H, spp_step, device=local, rank=rank, world=world, stream=stream, spp_per_wave=args.spp_per_wave)
+    rr = B200Renderer(fs, W, H, spp_step, device=local, rank=rank, world=world, stream=stream, spp_per_wave=args.spp_per_wave,
+                      tight_bvh={"auto": None, "on": True, "off": False}[args.tight_bvh])
 
     def e2e_step():
         rr.update_scene(fs)
@@ -331,6 +340,7 @@ def main():
                             "crt_resolve_rgba8 into host memory; host buffers are pageable numpy arrays"},
             "gpu_launches": int(launches),
             "stage_ms": stage,
+            "tight_bvh": {"wide_nodes": tight_nodes, "split_triangles": tight_always, "per_ray": per_ray},
             "roofline": {"bound": "hbm", "kernel": "k_extend+k_shadow (BVH traversal)", "achieved": round(achieved, 2) if achieved else None,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
                          "traffic": traffic, "algorithmic_bytes_per_launch": round((rays / world) * a_ray / max(n_trav_launches, 1), 0),

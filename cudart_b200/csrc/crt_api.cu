@@ -73,7 +73,8 @@ struct crt_ctx {
     DWave wv{};
     WideStats wide_stats{};
     // scene
-    DevBuf<float4> wide, tri_isect, tri_shade, mats, light_boxes;
+    DevBuf<float4> wide, tri_isect, tri_shade, tri_tight, mats, light_boxes;
+    uint32_t tight_split = 0, tight_nodes = 0;
     DevBuf<uint32_t> lights, tex_dims, tex_offsets;
     DevBuf<float> tex_data;
     // wave
@@ -140,13 +141,69 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     for (uint32_t k = 0; k < s->n_lights; k++)
         if (s->light_indices[k] >= s->n_tris) return (fail(CRT_ERR_INVALID, "scene: light index out of range"));
     std::vector<WideNode> wide;
+    std::vector<RefNode> ref_tree;          // the binary tree behind `wide`, for the cost comparison below
     {
         std::vector<RefNode> clustered;
         if (!(c->flags & CRT_FLAG_REFERENCE_TOPOLOGY)) recluster_leaves(nodes, s->n_nodes, clustered);
+        ref_tree = clustered.empty() ? std::vector<RefNode>(nodes, nodes + s->n_nodes) : clustered;
         c->wide_stats = clustered.empty() ? flatten_wide(nodes, s->n_nodes, tris, s->n_tris, wide)
                                           : flatten_wide(clustered.data(), (uint32_t)clustered.size(), tris, s->n_tris, wide);
     }
     if (3 * c->wide_stats.depth + 4 > 64) return (fail(CRT_ERR_LIMIT, "scene: wide BVH depth %u exceeds the traversal stack", c->wide_stats.depth));
+    // ---- tight per-triangle BVH in front of the reference-leaf tree (host_scene.h) ----
+    TightBvh tight;
+    F3 region_lo{FLT_MAX, FLT_MAX, FLT_MAX}, region_hi{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    uint32_t n_tight_wide = 0;
+    c->tight_split = c->tight_nodes = 0;
+    if (!(c->flags & (CRT_FLAG_NO_TIGHT_BVH | CRT_FLAG_EXACT_VISIT))) {
+        // region: every vertex and the camera, grown by 5 % of the diagonal (hit points on the scene's hull round outwards)
+        auto grow = [&](double x, double y, double z) {
+            region_lo = {std::min(region_lo.x, (float)x), std::min(region_lo.y, (float)y), std::min(region_lo.z, (float)z)};
+            region_hi = {std::max(region_hi.x, (float)x), std::max(region_hi.y, (float)y), std::max(region_hi.z, (float)z)};
+        };
+        bool finite = true;
+        for (uint32_t i = 0; i < s->n_tris; i++) {
+            const RefTriangle& t = tris[i];
+            grow(t.v1.x, t.v1.y, t.v1.z);
+            grow((double)t.v1.x + t.e1.x, (double)t.v1.y + t.e1.y, (double)t.v1.z + t.e1.z);
+            grow((double)t.v1.x + t.e2.x, (double)t.v1.y + t.e2.y, (double)t.v1.z + t.e2.z);
+        }
+        const RefCamera* cam = (const RefCamera*)s->camera;
+        grow(cam->eye.x, cam->eye.y, cam->eye.z);
+        const double dx = (double)region_hi.x - region_lo.x, dy = (double)region_hi.y - region_lo.y, dz = (double)region_hi.z - region_lo.z;
+        const double m = 0.05 * std::sqrt(dx * dx + dy * dy + dz * dz) + std::fabs((double)cam->apertureWidth) + 1e-3;
+        finite = std::isfinite(m) && m < 1e7;
+        if (finite) {
+            region_lo = {(float)(region_lo.x - m), (float)(region_lo.y - m), (float)(region_lo.z - m)};
+            region_hi = {(float)(region_hi.x + m), (float)(region_hi.y + m), (float)(region_hi.z + m)};
+            build_tight_bvh(tris, s->n_tris, nodes, s->n_nodes, region_lo, region_hi, tight);
+            // Per reference leaf the builder already chose between individually inflated triangles and the leaf behind its
+            // own box, and it may merge several reference leaves into one tight leaf (the gate keeps that exact), which the
+            // reference-leaf tree cannot.  Use it unless the surface-area-heuristic cost (expected node visits x their
+            // measured weight + triangle tests of a random line) says the reference-leaf tree is cheaper.
+            const SahCost tc = sah_cost(tight.nodes.data(), (uint32_t)tight.nodes.size(), region_lo, region_hi);
+            const SahCost ref_cost = sah_cost(ref_tree.data(), (uint32_t)ref_tree.size(), region_lo, region_hi);
+            const bool cheaper = kTightTraversalCost * tc.nodes + tc.tris < kTightTraversalCost * ref_cost.nodes + ref_cost.tris;
+            const bool want = (c->flags & CRT_FLAG_TIGHT_BVH) || cheaper;
+            if (!want || tight.nodes.empty()) tight = TightBvh();
+        }
+    }
+    if (!tight.nodes.empty()) {
+        std::vector<WideNode> tw;
+        const WideStats ts = flatten_wide(tight.nodes.data(), (uint32_t)tight.nodes.size(), tight.tris.data(), s->n_tris, tw);
+        if (3 * ts.depth + 4 > 64) {
+            tight = TightBvh();
+        } else {
+            n_tight_wide = (uint32_t)tw.size();
+            for (WideNode& w : wide)                                   // the reference-leaf tree moves behind the tight one
+                for (int k = 0; k < 4; k++)
+                    if (w.child[k] >= 0 && w.child[k] != kEmptyChild) w.child[k] += (int32_t)n_tight_wide;
+            tw.insert(tw.end(), wide.begin(), wide.end());
+            wide.swap(tw);
+            c->tight_split = tight.n_split;
+            c->tight_nodes = n_tight_wide;
+        }
+    }
     std::vector<TriIsect> isect;
     std::vector<TriShade> shade;
     make_tri_records(tris, s->n_tris, nodes, s->n_nodes, isect, shade);
@@ -169,6 +226,8 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     UP(wide, wide.data(), wide.size() * 8);
     UP(tri_isect, isect.data(), isect.size() * 3);
     UP(tri_shade, shade.data(), shade.size() * 5);
+    if (n_tight_wide) { UP(tri_tight, tight.records.data(), tight.records.size() * 5); }
+    else c->tri_tight.release();
     UP(mats, mats.data(), mats.size());
     UP(lights, s->light_indices, s->n_lights);
     std::vector<float4> lboxes(2 * (size_t)s->n_lights);
@@ -202,8 +261,13 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     // when only the top fits (monkeys: 288 of 1058 nodes) the mixed smem/global fetch diverges and costs 3.7 %.
     // Policy: stage iff the whole tree fits, unless forced either way.
     sc.n_smem_nodes = 0;
-    if (!(c->flags & CRT_FLAG_NO_SMEM_NODES) && (wide.size() <= kMaxSmemNodes || (c->flags & CRT_FLAG_SMEM_TOP_LEVELS)))
-        sc.n_smem_nodes = std::min<uint32_t>((uint32_t)wide.size(), kMaxSmemNodes);
+    const size_t n_front = n_tight_wide ? n_tight_wide : wide.size();      // the tree the render path's rays walk
+    if (!(c->flags & CRT_FLAG_NO_SMEM_NODES) && (n_front <= kMaxSmemNodes || (c->flags & CRT_FLAG_SMEM_TOP_LEVELS)))
+        sc.n_smem_nodes = std::min<uint32_t>((uint32_t)n_front, kMaxSmemNodes);
+    sc.tri_tight = n_tight_wide ? c->tri_tight.p : nullptr;
+    sc.ref_root = n_tight_wide;
+    sc.region_lo[0] = region_lo.x; sc.region_lo[1] = region_lo.y; sc.region_lo[2] = region_lo.z;
+    sc.region_hi[0] = region_hi.x; sc.region_hi[1] = region_hi.y; sc.region_hi[2] = region_hi.z;
     sc.n_wide = (uint32_t)wide.size(); sc.n_tris = s->n_tris; sc.n_mats = s->n_mats; sc.n_lights = s->n_lights;
     sc.n_tex = s->n_tex; sc.tex_texels = s->tex_texels; sc.lights_area = s->lights_area;
     memcpy(&sc.cam, s->camera, sizeof(RefCamera));
@@ -547,6 +611,38 @@ int crt_wide_bvh(const void* nodes, uint32_t n_nodes, void* wide_out, uint32_t c
     flatten_wide(clustered.data(), (uint32_t)clustered.size(), nullptr, 0, wide);
     *n_wide_out = (uint32_t)wide.size();
     if (wide_out) memcpy(wide_out, wide.data(), std::min<size_t>(cap, wide.size()) * sizeof(WideNode));
+    return CRT_OK;
+}
+
+
+int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t n_nodes, const float* region, float* tri_boxes_out,
+                  uint32_t* n_split_out, uint32_t* n_tight_nodes_out, uint32_t* n_wide_out, double* sah_out) {
+    if (!tris || !nodes || !region) return fail(CRT_ERR_INVALID, "crt_tight_bvh: null argument");
+    TightBvh tb;
+    build_tight_bvh((const RefTriangle*)tris, n_tris, (const RefNode*)nodes, n_nodes, F3{region[0], region[1], region[2]},
+                    F3{region[3], region[4], region[5]}, tb);
+    if (tri_boxes_out && tb.boxes.size() == 6 * (size_t)n_tris) memcpy(tri_boxes_out, tb.boxes.data(), tb.boxes.size() * sizeof(float));
+    if (n_split_out) *n_split_out = tb.n_split;
+    if (n_tight_nodes_out) *n_tight_nodes_out = (uint32_t)tb.nodes.size();
+    if (sah_out) {      // (nodes, triangles) expected per random line: tight tree, then the re-clustered reference-leaf tree
+        std::vector<RefNode> clustered;
+        recluster_leaves((const RefNode*)nodes, n_nodes, clustered);
+        const F3 rl{region[0], region[1], region[2]}, rh{region[3], region[4], region[5]};
+        const SahCost a = sah_cost(tb.nodes.data(), (uint32_t)tb.nodes.size(), rl, rh), b = sah_cost(clustered.data(), (uint32_t)clustered.size(), rl, rh);
+        sah_out[0] = a.nodes; sah_out[1] = a.tris; sah_out[2] = b.nodes; sah_out[3] = b.tris;
+    }
+    if (n_wide_out) {
+        std::vector<WideNode> tw;
+        if (!tb.nodes.empty()) flatten_wide(tb.nodes.data(), (uint32_t)tb.nodes.size(), tb.tris.data(), n_tris, tw);
+        *n_wide_out = (uint32_t)tw.size();
+    }
+    return CRT_OK;
+}
+
+int crt_tight_info(const crt_ctx* c, uint32_t* n_tight_wide_out, uint32_t* n_split_out) {
+    if (!c) return fail(CRT_ERR_INVALID, "crt_tight_info: null ctx");
+    if (n_tight_wide_out) *n_tight_wide_out = c->tight_nodes;
+    if (n_split_out) *n_split_out = c->tight_split;
     return CRT_OK;
 }
 

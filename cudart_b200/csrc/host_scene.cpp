@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace crt {
@@ -476,6 +477,285 @@ WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, const RefTriangle
     }
     st.n_wide = (uint32_t)out.size();
     return st;
+}
+
+// ---- tight triangle BVH ---------------------------------------------------------------------------------------------
+namespace {
+// A primitive of the tight tree: one triangle with its inflated box, or (group) all the triangles of a reference leaf that
+// are better off behind the leaf's own exact box.
+struct TightPrim { uint32_t first, count; F3 mn, mx, c; };     // members[first .. first + count)
+
+struct TightBuilder {
+    std::vector<TightPrim> prims;
+    std::vector<uint32_t> members;               // triangle indices, grouped per primitive
+    std::vector<RefNode> out;
+    std::vector<uint32_t> order;                 // tight slot -> original triangle index
+
+    static double area(const F3& mn, const F3& mx) {
+        const double dx = std::max(0.0, (double)mx.x - mn.x), dy = std::max(0.0, (double)mx.y - mn.y), dz = std::max(0.0, (double)mx.z - mn.z);
+        return dx * dy + dy * dz + dz * dx;
+    }
+    uint32_t build(uint32_t lo, uint32_t hi) {
+        const uint32_t my = (uint32_t)out.size();
+        out.emplace_back();
+        F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}, cmn = mn, cmx = mx;
+        uint32_t weight = 0;
+        for (uint32_t i = lo; i < hi; i++) {
+            mn = lo3(mn, prims[i].mn); mx = hi3(mx, prims[i].mx);
+            cmn = lo3(cmn, prims[i].c); cmx = hi3(cmx, prims[i].c);
+            weight += prims[i].count;
+        }
+        const uint32_t n = hi - lo;
+        auto make_leaf = [&]() {
+            RefNode& nd = out[my];
+            std::memset(&nd, 0, sizeof nd);
+            nd.mn = mn; nd.mx = mx;
+            nd.offset = (int32_t)order.size();
+            nd.nTris = (int16_t)weight;
+            for (uint32_t i = lo; i < hi; i++)
+                for (uint32_t m = 0; m < prims[i].count; m++) order.push_back(members[prims[i].first + m]);
+            return my;
+        };
+        // SAH with the traversal cost measured on B200: one wide-node visit costs about as much as eight triangle
+        // tests (profiles/r01s_*: a wide node covers ~3 binary nodes, hence 3 per binary node), so leaves of up to 8
+        // triangles beat the reference's <= 3: cornellSphere 1649 -> 1950 Msamples/s, monkeys 775 -> 815, terrain 1M 324 -> 354.
+        constexpr double kTrav = kTightTraversalCost;
+        constexpr uint32_t kMaxLeaf = 8;
+        const bool leaf_ok = weight <= 32767u;
+        if (n == 1 || (leaf_ok && weight <= 2)) return make_leaf();
+        constexpr int kBins = 16;
+        int bestAxis = -1, bestSplit = 0;
+        double bestCost = DBL_MAX;
+        for (int ax = 0; ax < 3; ax++) {
+            const float c0 = axis_of(cmn, ax), c1 = axis_of(cmx, ax);
+            if (!(c1 > c0)) continue;
+            struct Bin { F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}; uint32_t w = 0; } bins[kBins];
+            const float scale = kBins / (c1 - c0);
+            for (uint32_t i = lo; i < hi; i++) {
+                int b = (int)((axis_of(prims[i].c, ax) - c0) * scale);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                bins[b].mn = lo3(bins[b].mn, prims[i].mn); bins[b].mx = hi3(bins[b].mx, prims[i].mx);
+                bins[b].w += prims[i].count;
+            }
+            double rightA[kBins]; uint32_t rightW[kBins];
+            F3 rmn{FLT_MAX, FLT_MAX, FLT_MAX}, rmx{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            uint32_t rw = 0;
+            for (int b = kBins - 1; b > 0; b--) {
+                rmn = lo3(rmn, bins[b].mn); rmx = hi3(rmx, bins[b].mx); rw += bins[b].w;
+                rightA[b] = rw ? area(rmn, rmx) : 0.0; rightW[b] = rw;
+            }
+            F3 lmn{FLT_MAX, FLT_MAX, FLT_MAX}, lmx{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            uint32_t lw = 0;
+            for (int b = 0; b < kBins - 1; b++) {
+                lmn = lo3(lmn, bins[b].mn); lmx = hi3(lmx, bins[b].mx); lw += bins[b].w;
+                if (!lw || !rightW[b + 1]) continue;
+                const double cost = area(lmn, lmx) * lw + rightA[b + 1] * rightW[b + 1];
+                if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestSplit = b; }
+            }
+        }
+        // leaf when splitting does not pay and the leaf stays small
+        if (leaf_ok && weight <= kMaxLeaf && (bestAxis < 0 || bestCost + kTrav * area(mn, mx) >= area(mn, mx) * (double)weight)) return make_leaf();
+        uint32_t mid = lo;
+        if (bestAxis >= 0) {
+            const float c0 = axis_of(cmn, bestAxis), scale = kBins / (axis_of(cmx, bestAxis) - c0);
+            TightPrim* m = std::partition(prims.data() + lo, prims.data() + hi, [&](const TightPrim& p) {
+                int b = (int)((axis_of(p.c, bestAxis) - c0) * scale);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                return b <= bestSplit;
+            });
+            mid = (uint32_t)(m - prims.data());
+        }
+        if (mid == lo || mid == hi) {
+            if (leaf_ok && weight <= kMaxLeaf) return make_leaf();
+            mid = (lo + hi) / 2;
+        }
+        build(lo, mid);
+        const uint32_t second = build(mid, hi);
+        RefNode& nd = out[my];
+        std::memset(&nd, 0, sizeof nd);
+        nd.mn = mn; nd.mx = mx;
+        nd.offset = (int32_t)second;
+        return my;
+    }
+};
+inline float round_down(double v) { float f = (float)v; return (double)f > v ? std::nextafterf(f, -INFINITY) : f; }
+inline float round_up(double v) { float f = (float)v; return (double)f < v ? std::nextafterf(f, INFINITY) : f; }
+
+// Inflated box of one triangle for origins inside [region_lo, region_hi]; false when the fp32 test admits no useful bound.
+bool inflated_box(const RefTriangle& t, const F3& region_lo, const F3& region_hi, F3& mn_out, F3& mx_out) {
+    // The triangle the reference intersects is (v1, v1 + e1, v1 + e2) in REAL arithmetic on the stored fp32 values.
+    const double p[3][3] = {{t.v1.x, t.v1.y, t.v1.z},
+                            {(double)t.v1.x + t.e1.x, (double)t.v1.y + t.e1.y, (double)t.v1.z + t.e1.z},
+                            {(double)t.v1.x + t.e2.x, (double)t.v1.y + t.e2.y, (double)t.v1.z + t.e2.z}};
+    auto len = [](const F3& v) { return std::sqrt((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z); };
+    const F3 e3{t.e2.x - t.e1.x, t.e2.y - t.e1.y, t.e2.z - t.e1.z};
+    const double l1 = len(t.e1), l2 = len(t.e2), L = std::max(l1, std::max(l2, len(e3)));
+    // |T| = |origin - v1| <= D for every origin inside the region
+    double D2 = 0;
+    const double lo[3] = {region_lo.x, region_lo.y, region_lo.z}, hi[3] = {region_hi.x, region_hi.y, region_hi.z};
+    for (int k = 0; k < 3; k++) { const double m = std::max(std::fabs(p[0][k] - lo[k]), std::fabs(hi[k] - p[0][k])); D2 += m * m; }
+    const double D = std::sqrt(D2);
+    // Forward error of the accepted fp32 barycentrics (|det| >= 1e-5, |d| <= 1, eps = 2^-24):
+    //   |du| |e1| <= (8 eps |T| + 7 eps |u| |e1|) |e1||e2| / 1e-5 <= 0.8 s |T| + 0.7 s L,  s = 10 eps |e1||e2| / 1e-5
+    // (same s as triangle_cull_bound) and likewise for v: the REAL intersection point of the ray's line with the
+    // triangle's plane lies within 1.6 s D + 1.4 s L of the triangle, measured IN the plane.  pad rounds that up to
+    // 2 s (D + L); iso covers the rounding of the box test itself (3 eps D per plane) with a 50x margin.
+    const double s = 0.06 * l1 * l2;
+    const double pad = 2.0 * s * (D + L), iso = 1e-5 * D + 1e-3 * pad;
+    if (!(s < 0.25) || !std::isfinite(pad) || !std::isfinite(iso)) return false;
+    // in-plane disc of radius pad: half extent pad * sqrt(1 - n_k^2) on axis k
+    const double nx = (double)t.e1.y * t.e2.z - (double)t.e1.z * t.e2.y, ny = (double)t.e1.z * t.e2.x - (double)t.e1.x * t.e2.z,
+                 nz = (double)t.e1.x * t.e2.y - (double)t.e1.y * t.e2.x;
+    const double nl = std::sqrt(nx * nx + ny * ny + nz * nz);
+    double ext[3] = {pad, pad, pad};
+    if (nl > 1e-3 * l1 * l2 && nl > 0) {
+        const double n[3] = {nx / nl, ny / nl, nz / nl};
+        for (int k = 0; k < 3; k++) ext[k] = pad * std::sqrt(std::max(0.0, 1.0 - n[k] * n[k])) * 1.001;
+    }
+    double mn[3], mx[3];
+    for (int k = 0; k < 3; k++) {
+        mn[k] = std::min(p[0][k], std::min(p[1][k], p[2][k])) - ext[k] - iso;
+        mx[k] = std::max(p[0][k], std::max(p[1][k], p[2][k])) + ext[k] + iso;
+    }
+    mn_out = {round_down(mn[0]), round_down(mn[1]), round_down(mn[2])};
+    mx_out = {round_up(mx[0]), round_up(mx[1]), round_up(mx[2])};
+    return true;
+}
+}  // namespace
+
+void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* ref_nodes, uint32_t n_ref_nodes,
+                     const F3& region_lo, const F3& region_hi, TightBvh& out) {
+    out = TightBvh();
+    if (n_tris == 0) return;
+    out.boxes.assign(6 * (size_t)n_tris, 0.f);
+    TightBuilder tb, ub;                    // bounded primitives / groups of triangles without a distance bound
+    tb.prims.reserve(n_tris);
+    tb.members.reserve(n_tris);
+    std::vector<uint32_t> leaf_of(n_tris, 0xffffffffu);
+    auto set_box = [&](uint32_t i, const F3& mn, const F3& mx) {
+        float* b = &out.boxes[6 * (size_t)i];
+        b[0] = mn.x; b[1] = mn.y; b[2] = mn.z; b[3] = mx.x; b[4] = mx.y; b[5] = mx.z;
+    };
+    auto add_prim = [](TightBuilder& bd, const std::vector<uint32_t>& m, const F3& mn, const F3& mx) {
+        TightPrim pr;
+        pr.first = (uint32_t)bd.members.size(); pr.count = (uint32_t)m.size();
+        pr.mn = mn; pr.mx = mx;
+        pr.c = {(mn.x + mx.x) * 0.5f, (mn.y + mx.y) * 0.5f, (mn.z + mx.z) * 0.5f};
+        bd.members.insert(bd.members.end(), m.begin(), m.end());
+        bd.prims.push_back(pr);
+    };
+    std::vector<uint32_t> bounded, unbounded, one(1);
+    std::vector<F3> bmn, bmx;
+    for (uint32_t k = 0; k < n_ref_nodes; k++) {
+        const RefNode& lf = ref_nodes[k];
+        if (lf.nTris <= 0) continue;
+        // The leaf's own box in min/max order (the reference's slab test sorts each axis, renderer.cu:339-343); a box that
+        // is not finite is replaced by the region: the gate in the kernel stays the exact reference box either way.
+        F3 gmn = lo3(lf.mn, lf.mx), gmx = hi3(lf.mn, lf.mx);
+        const float gb[6] = {gmn.x, gmn.y, gmn.z, gmx.x, gmx.y, gmx.z};
+        bool finite = true;
+        for (float f : gb) finite = finite && std::isfinite(f);
+        if (!finite) { gmn = region_lo; gmx = region_hi; }
+        bounded.clear(); unbounded.clear(); bmn.clear(); bmx.clear();
+        double split_cost = 0;
+        for (uint32_t i = 0; i < (uint32_t)(uint16_t)lf.nTris && (uint32_t)lf.offset + i < n_tris; i++) {
+            const uint32_t idx = (uint32_t)lf.offset + i;
+            if (leaf_of[idx] != 0xffffffffu) continue;                       // overlapping leaves: first owner wins
+            leaf_of[idx] = k;
+            F3 mn, mx;
+            if (inflated_box(tris[idx], region_lo, region_hi, mn, mx)) {
+                bounded.push_back(idx); bmn.push_back(mn); bmx.push_back(mx);
+                split_cost += TightBuilder::area(mn, mx);
+            } else {
+                unbounded.push_back(idx);
+                out.n_unbounded++;
+            }
+        }
+        if (!unbounded.empty()) {
+            add_prim(ub, unbounded, gmn, gmx);
+            for (uint32_t i : unbounded) set_box(i, gmn, gmx);
+        }
+        if (bounded.empty()) continue;
+        // Individually inflated triangles, or the whole leaf behind its exact box?  SAH: sum of the inflated areas (plus
+        // the extra nodes and gate tests, hence the 0.7) against the leaf area times its triangle count.
+        const double group_cost = TightBuilder::area(gmn, gmx) * (double)bounded.size();
+        if (split_cost < 0.7 * group_cost) {
+            for (size_t j = 0; j < bounded.size(); j++) {
+                one[0] = bounded[j];
+                add_prim(tb, one, bmn[j], bmx[j]);
+                set_box(bounded[j], bmn[j], bmx[j]);
+            }
+            out.n_split += (uint32_t)bounded.size();
+        } else {
+            add_prim(tb, bounded, gmn, gmx);
+            for (uint32_t i : bounded) set_box(i, gmn, gmx);
+        }
+    }
+    if (tb.prims.empty() && ub.prims.empty()) { out = TightBvh(); return; }
+    // One tree: root = (subtree of the groups without a distance bound, subtree of everything else).  Keeping the former
+    // apart keeps their (A = 0, B = inf) cull bound out of every other node's bound (flatten_wide takes the loosest).
+    std::vector<RefNode>& nodes = out.nodes;
+    std::vector<uint32_t> order;
+    auto append = [&](TightBuilder& bd) {          // build bd's tree and splice it behind `nodes` / `order`
+        bd.out.reserve(2 * bd.prims.size());
+        bd.build(0, (uint32_t)bd.prims.size());
+        const uint32_t nbase = (uint32_t)nodes.size(), obase = (uint32_t)order.size();
+        for (RefNode nd : bd.out) {
+            if (nd.nTris > 0) nd.offset += (int32_t)obase; else nd.offset += (int32_t)nbase;
+            nodes.push_back(nd);
+        }
+        order.insert(order.end(), bd.order.begin(), bd.order.end());
+        return nbase;
+    };
+    if (!tb.prims.empty() && !ub.prims.empty()) {
+        nodes.emplace_back();
+        append(ub);
+        const uint32_t second = append(tb);
+        RefNode& rt = nodes[0];
+        std::memset(&rt, 0, sizeof rt);
+        rt.mn = lo3(nodes[1].mn, nodes[second].mn); rt.mx = hi3(nodes[1].mx, nodes[second].mx);
+        rt.offset = (int32_t)second;
+    } else {
+        append(tb.prims.empty() ? ub : tb);
+    }
+    const uint32_t n_used = (uint32_t)order.size();          // triangles in no reference leaf are never reached: left out
+    out.records.resize(n_used);
+    out.tris.resize(n_used);
+    for (uint32_t slot = 0; slot < n_used; slot++) {
+        const uint32_t i = order[slot];
+        const RefTriangle& t = tris[i];
+        TightRecord& r = out.records[slot];
+        std::memset(&r, 0, sizeof r);
+        r.v1[0] = t.v1.x; r.v1[1] = t.v1.y; r.v1[2] = t.v1.z;
+        r.e1[0] = t.e1.x; r.e1[1] = t.e1.y; r.e1[2] = t.e1.z;
+        r.e2[0] = t.e2.x; r.e2[1] = t.e2.y; r.e2[2] = t.e2.z;
+        r.origIdx = i;
+        const RefNode& lf = ref_nodes[leaf_of[i]];
+        r.leafFirst = (uint32_t)lf.offset;
+        r.gateLo[0] = lf.mn.x; r.gateLo[1] = lf.mn.y; r.gateLo[2] = lf.mn.z;
+        r.gateHiX = lf.mx.x; r.gateHiY = lf.mx.y; r.gateHiZ = lf.mx.z;
+        out.tris[slot] = t;
+    }
+}
+
+SahCost sah_cost(const RefNode* nodes, uint32_t n_nodes, const F3& clip_lo, const F3& clip_hi) {
+    SahCost c;
+    if (n_nodes == 0) return c;
+    auto area = [&](const F3& mn, const F3& mx) {
+        const double dx = std::max(0.0, (double)std::min(mx.x, clip_hi.x) - std::max(mn.x, clip_lo.x)),
+                     dy = std::max(0.0, (double)std::min(mx.y, clip_hi.y) - std::max(mn.y, clip_lo.y)),
+                     dz = std::max(0.0, (double)std::min(mx.z, clip_hi.z) - std::max(mn.z, clip_lo.z));
+        return dx * dy + dy * dz + dz * dx;
+    };
+    const double root = area(clip_lo, clip_hi);
+    if (!(root > 0) || !std::isfinite(root)) return c;
+    for (uint32_t k = 0; k < n_nodes; k++) {
+        const double a = area(lo3(nodes[k].mn, nodes[k].mx), hi3(nodes[k].mn, nodes[k].mx)) / root;
+        if (!std::isfinite(a)) continue;
+        if (nodes[k].nTris > 0) c.tris += a * (double)(uint16_t)nodes[k].nTris;
+        else c.nodes += a;
+    }
+    return c;
 }
 
 void make_tri_records(const RefTriangle* tris, uint32_t n, const RefNode* nodes, uint32_t n_nodes,

@@ -91,6 +91,41 @@ CullBound triangle_cull_bound(const RefTriangle& t);
 // aux word of a WideNode child: bf16(A) rounded down in the high half, bf16(B) rounded up in the low half
 uint32_t pack_cull_bound(CullBound b);
 
+// ---- tight triangle BVH ("fast path" acceleration structure) ------------------------------------------------------
+// The reference's leaves decide which triangles a ray may hit, but they are poor spatial clusters (on the 1M-triangle
+// terrain a <= 3-triangle leaf spans 0.6 x 1.9 units of a 0.085-unit grid: 358 triangle tests per ray).  The tight BVH is
+// built over the individual triangles instead, with every triangle box inflated far enough that any ray whose fp32
+// Moeller-Trumbore test (geometry.cu:38-65) ACCEPTS the triangle is guaranteed to pass the box; a candidate found this way
+// still has to pass the reference's own slab test of its reference leaf box (the "gate") before it counts.  Same accepted
+// set as the reference traversal, far fewer candidates.
+struct TightRecord {            // 80 B = 5 x float4
+    float v1[3]; uint32_t origIdx;          // index in the reference's (BVH-ordered) triangle array = what hits report
+    float e1[3]; uint32_t leafFirst;        // firstTriOffset of the reference leaf (tie key)
+    float e2[3]; uint32_t pad0;
+    float gateLo[3]; float gateHiX;         // the reference leaf's exact box
+    float gateHiY, gateHiZ; uint32_t pad1[2];
+};
+static_assert(sizeof(TightRecord) == 80, "tight triangle record");
+// region = box that contains every ray origin the bound is valid for (scene box united with the camera), see DESIGN.md
+struct TightBvh {
+    std::vector<RefNode> nodes;             // binary tree in the reference's pre-order layout over the tight order
+    std::vector<TightRecord> records;       // triangles in tight order
+    std::vector<RefTriangle> tris;          // same order, for the cull bounds of flatten_wide
+    std::vector<float> boxes;               // per ORIGINAL triangle index, lo.xyz hi.xyz: the box a ray must pass before the
+                                            // triangle is tested (its own inflated box, or its reference leaf's exact box)
+    uint32_t n_unbounded = 0;               // triangles too large for a distance bound (kept behind their reference leaf's box)
+    uint32_t n_split = 0;                   // triangles that got their own inflated box
+};
+void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* ref_nodes, uint32_t n_ref_nodes,
+                     const F3& region_lo, const F3& region_hi, TightBvh& out);
+
+// Surface-area-heuristic cost of a binary tree in the reference's pre-order layout: expected (interior nodes visited,
+// triangles tested) by a random line that crosses the clip box (node boxes are clipped to it, so that two trees over
+// the same scene are measured against the same set of lines).
+struct SahCost { double nodes = 0, tris = 0; };
+constexpr double kTightTraversalCost = 3.0;      // cost of visiting one binary node, in triangle tests (measured, see host_scene.cpp)
+SahCost sah_cost(const RefNode* nodes, uint32_t n_nodes, const F3& clip_lo, const F3& clip_hi);
+
 void make_tri_records(const RefTriangle* tris, uint32_t n, const RefNode* nodes, uint32_t n_nodes,
                       std::vector<TriIsect>& isect, std::vector<TriShade>& shade);
 

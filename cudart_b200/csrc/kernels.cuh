@@ -12,6 +12,7 @@ struct DScene {
     const float4* wide;        // n_wide x 8 float4  (WideNode)
     const float4* tri_isect;   // n_tris x 3 float4  (TriIsect)
     const float4* tri_shade;   // n_tris x 5 float4  (TriShade)
+    const float4* tri_tight;   // n_tris x 5 float4  (TightRecord, tight-BVH order); null when the tight BVH is off
     const float4* mats;        // n_mats x 4 float4: (kd, bsdf) (ka, texKdIdx) (ks, 0) (ns, ni, diffuseCoefficient, 0)
     const uint32_t* lights;
     const float4* light_boxes; // per light: the reference leaf box holding it (lo.xyz, hi.xyz), for the shadow seed
@@ -22,6 +23,10 @@ struct DScene {
     uint32_t n_smem_nodes;     // the first n_smem_nodes wide nodes (top levels, breadth-first) are staged in shared memory
     float lights_area;
     int coords_bounded;        // every node/triangle coordinate is finite and below 1e8 in magnitude
+    // Tight BVH (host_scene.h): its wide nodes are [0, ref_root), the reference-leaf tree starts at ref_root.  Rays that
+    // qualify (culling allowed, origin inside the region the inflation was computed for) start at node 0.
+    uint32_t ref_root;
+    float region_lo[3], region_hi[3];
     RefCamera cam;
 };
 

@@ -45,6 +45,21 @@ def wide_bvh(nodes: np.ndarray) -> np.ndarray:
     return out
 
 
+def tight_bvh(tris: np.ndarray, nodes: np.ndarray, region_lo, region_hi, sah: bool = False):
+    """The box a ray (starting inside the region) must pass before each triangle is tested in the tight BVH (f32[n, 6],
+    reference triangle order), plus (individually boxed triangles, binary nodes, wide nodes).  Introspection for tests."""
+    tris = np.ascontiguousarray(tris, TRIANGLE_DTYPE)
+    nodes = np.ascontiguousarray(nodes, NODE_DTYPE)
+    region = np.asarray(list(region_lo) + list(region_hi), np.float32)
+    boxes = np.zeros((tris.shape[0], 6), np.float32)
+    nb, nn, nw = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    cost = np.zeros(4, np.float64)      # SAH (nodes, triangles) per random line: tight tree, reference-leaf tree
+    capi.check(capi.lib().crt_tight_bvh(tris.ctypes.data, tris.shape[0], nodes.ctypes.data, nodes.shape[0], region.ctypes.data,
+                                        boxes.ctypes.data, C.byref(nb), C.byref(nn), C.byref(nw), cost.ctypes.data))
+    info = (int(nb.value), int(nn.value), int(nw.value))
+    return (boxes, info, cost) if sah else (boxes, info)
+
+
 def assemble(tris, positions, mat_floats, mat_indices, camera, tex_dims=None, tex_offsets=None, tex_data=None,
              width=0, height=0) -> FlatScene:
     """OBJ-order triangles + unscaled material table -> the flat scene the renderers consume."""

@@ -73,6 +73,8 @@ typedef struct crt_options {
 #define CRT_FLAG_REFERENCE_TOPOLOGY 8u /* keep the reference's interior BVH structure (no SAH re-clustering of its leaves) */
 #define CRT_FLAG_NO_SMEM_NODES 16u /* never stage BVH nodes in shared memory (default: staged when the whole wide tree fits) */
 #define CRT_FLAG_SMEM_TOP_LEVELS 32u /* stage the top levels even when the tree does not fit entirely (A/B measurements) */
+#define CRT_FLAG_TIGHT_BVH 64u   /* force the tight per-triangle BVH (default: used when few triangles are too large for it) */
+#define CRT_FLAG_NO_TIGHT_BVH 128u /* never use the tight BVH: traverse the reference's leaves only            */
 #define CRT_FLAG_STATS 4u        /* count wide-node fetches and triangle tests (slows traversal a little)  */
 
 typedef struct crt_ray { float ox, oy, oz, dx, dy, dz, tmin, tmax; } crt_ray;   /* == reference Ray       */
@@ -147,6 +149,15 @@ int crt_build_lights(void* tris, uint32_t n_tris, float* mat_floats, const int32
                      uint32_t* light_indices_out, uint32_t* n_lights_out, float* lights_area_out);
 /* Introspection of the wide (4-ary) flattening, for tests: writes up to cap 128-byte nodes. */
 int crt_wide_bvh(const void* nodes, uint32_t n_nodes, void* wide_out, uint32_t cap, uint32_t* n_wide_out);
+/* Introspection of the tight per-triangle BVH (no reference counterpart), for tests: region = lo.xyz, hi.xyz of
+ * the box that holds every ray origin; tri_boxes_out (6 floats per triangle, reference order) receives the box a ray must
+ * pass before the triangle is tested (the triangle's own inflated box, or its reference leaf's exact box when the leaf was
+ * kept whole); *n_split_out = triangles with their own box; binary / wide node counts; sah_out = surface-area-heuristic
+ * (nodes, triangles) per random line for the tight tree and for the re-clustered reference-leaf tree. */
+int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t n_nodes, const float* region, float* tri_boxes_out,
+                  uint32_t* n_split_out, uint32_t* n_tight_nodes_out, uint32_t* n_wide_out, double* sah_out /* 4 doubles or null */);
+/* Whether this context's render path walks the tight BVH: its wide-node count (0 = off) and individually boxed triangles. */
+int crt_tight_info(const crt_ctx* ctx, uint32_t* n_tight_wide_out, uint32_t* n_split_out);
 
 #ifdef __cplusplus
 }

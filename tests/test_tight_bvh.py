@@ -1,0 +1,106 @@
+"""Host side of the tight per-triangle BVH (cudart_b200/csrc/host_scene.cpp build_tight_bvh).
+
+The structure is only allowed to SKIP a triangle for a ray when the reference's fp32 Moeller-Trumbore test
+(geometry.cu:38-65) rejects it.  These tests pin that on the CPU: whenever the restated test accepts a triangle, the ray
+must pass the triangle's inflated box under the kernel's slab arithmetic - for the oracle's own path rays and for
+adversarial grazing rays whose determinant sits at the reference's 1e-5 acceptance threshold."""
+import numpy as np
+import pytest
+
+from conftest import SCENES
+from grazing import f32, grazing_rays, moeller_trumbore, region_of
+from oracle import orc
+
+
+def box_pass(boxes, o, d):
+    """The traversal kernel's min/max slab test (kernels.cu trace_queue, `fast` path) in numpy float32."""
+    with np.errstate(all="ignore"):
+        inv = (f32(1) / d).astype(f32)
+        a0 = ((boxes[:, :3] - o).astype(f32) * inv).astype(f32)
+        a1 = ((boxes[:, 3:] - o).astype(f32) * inv).astype(f32)
+        return np.minimum(a0, a1).max(1) <= np.maximum(a0, a1).min(1), np.all(np.abs(inv) < 1e28, 1)
+
+
+def leaf_boxes(fs):
+    """Per triangle: is it in a reference leaf, and that leaf's box in min/max order."""
+    in_leaf = np.zeros(len(fs.tris), bool)
+    box = np.zeros((len(fs.tris), 6), np.float32)
+    for nd in fs.nodes[fs.nodes["numTriangles"] > 0]:
+        sl = slice(int(nd["offset"]), int(nd["offset"]) + int(nd["numTriangles"]))
+        in_leaf[sl] = True
+        box[sl] = np.concatenate([np.minimum(nd["min"], nd["max"]), np.maximum(nd["min"], nd["max"])])
+    return in_leaf, box
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_accepted_grazing_hits_pass_the_inflated_box(golden, name):
+    from cudart_b200.scenebuild import tight_bvh
+    fs, _ = golden(name)
+    lo, hi = region_of(fs)
+    boxes, (n_big, n_nodes, n_wide) = tight_bvh(fs.tris, fs.nodes, lo, hi)
+    assert n_nodes > 0 and n_wide > 0
+    o, d, k = grazing_rays(fs, 200_000)
+    t = fs.tris
+    acc, _, _, _, det = moeller_trumbore(o, d, t["v1"][k], t["e1"][k], t["e2"][k])
+    passed, fast = box_pass(boxes[k], o, d)
+    acc &= fast
+    assert acc.sum() > 20_000 and (acc & (np.abs(det) < 3e-5)).sum() > 2_000      # the generator reaches the threshold regime
+    # a triangle with its own inflated box: every accepted hit passes it.  A triangle kept behind its reference leaf's box
+    # is only ever hit by the reference when that box passes - which then IS the box.
+    in_leaf, lbox = leaf_boxes(fs)
+    own = (~np.all(boxes == lbox, 1) & in_leaf)[k]
+    gate, _ = box_pass(lbox[k], o, d)
+    assert not (acc & own & ~passed).any()
+    assert not (acc & gate & ~passed).any()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_path_ray_winners_pass_their_inflated_box(golden, name):
+    from cudart_b200.scenebuild import tight_bvh
+    fs, _ = golden(name)
+    small = fs.with_resolution(64, 48)
+    lo, hi = region_of(small)
+    boxes, _ = tight_bvh(small.tris, small.nodes, lo, hi)
+    osc = orc.OracleScene(small)
+    _, rays = osc.render_accum(4, rng=orc.RNG_COUNTER, seed=11, threads=1, ray_log_cap=64 * 48 * 4 * 12)
+    want = osc.trace_closest(rays)
+    hit = want["tri"] != 0xFFFFFFFF
+    o, d = rays["o"][hit], rays["d"][hit]
+    assert np.all((o >= lo) & (o <= hi)), "path ray origins must stay inside the region the bound is valid for"
+    passed, fast = box_pass(boxes[want["tri"][hit]], o, d)
+    assert not (fast & ~passed).any()
+
+
+def test_boxes_contain_their_triangle_and_unsplit_leaves_keep_the_reference_box(golden):
+    from cudart_b200.scenebuild import tight_bvh
+    for name in SCENES:
+        fs, _ = golden(name)
+        lo, hi = region_of(fs)
+        boxes, (n_split, n_nodes, _) = tight_bvh(fs.tris, fs.nodes, lo, hi)
+        t = fs.tris
+        v1 = t["v1"].astype(np.float64)
+        in_leaf, leaf_box = leaf_boxes(fs)
+        own = ~np.all(boxes == leaf_box, 1) & in_leaf
+        assert own.sum() <= n_split <= in_leaf.sum()
+        for p in (v1, v1 + t["e1"], v1 + t["e2"]):          # an inflated box contains the real triangle
+            assert np.all(boxes[own, :3] <= p[own]) and np.all(p[own] <= boxes[own, 3:])
+
+
+def test_degenerate_and_huge_triangles_keep_their_reference_leaf_box(golden):
+    """Zero-area, huge and tiny triangles: no bound that is not deserved, no non-finite box."""
+    from cudart_b200.scenebuild import tight_bvh
+    from cudart_b200.scenefile import NODE_DTYPE, TRIANGLE_DTYPE
+    t = np.zeros(4, TRIANGLE_DTYPE)
+    t["v1"] = [[0, 0, 0], [1, 1, 1], [0, 0, 0], [2, 2, 2]]
+    t["e1"] = [[1, 0, 0], [100, 0, 0], [1, 0, 0], [1e-3, 0, 0]]
+    t["e2"] = [[0, 1, 0], [0, 100, 0], [2, 0, 0], [0, 1e-3, 0]]      # unit, huge, zero-area (collinear), tiny
+    nodes = np.zeros(1, NODE_DTYPE)
+    nodes["min"] = [[0, 0, 0]]
+    nodes["max"] = [[101, 101, 3]]
+    nodes["numTriangles"] = 4
+    boxes, (n_split, n_nodes, n_wide) = tight_bvh(t, nodes, [-10, -10, -10], [110, 110, 10])
+    assert np.all(boxes[1] == [0, 0, 0, 101, 101, 3])               # s >= 0.25: behind the leaf's own box
+    assert np.all(np.isfinite(boxes)) and n_nodes >= 1 and n_wide >= 1
+    ext = boxes[:, 3:] - boxes[:, :3]
+    assert np.all(ext[3] < 0.1) and np.all(ext[3] > 1e-3)            # a tiny triangle keeps a tiny (but padded) box
+    assert n_split >= 1
