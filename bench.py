@@ -72,15 +72,50 @@ def measured_peaks():
 
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe): NVML polled in-process every
+    20 ms (nvidia_ml_py), or an `nvidia-smi -lms 100` child when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, str(gpu_index)
+    def __init__(self, gpu_index, uuid=None):
+        self.rows, self.proc, self.gpu, self.uuid = [], None, str(gpu_index), uuid
+        self.sm, self.mx, self.reasons, self.stop, self.t, self.source = [], [], set(), threading.Event(), None, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(self.uuid)
+            except Exception:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(int(self.gpu))
+
+    def _poll_nvml(self, nv, h):
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while True:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(reasons_fn(h))
+                self.reasons.update(k for k, bit in self.BITS.items() if mask & bit)
+            except Exception:
+                pass
+            if self.stop.wait(0.02):
+                break
 
     def __enter__(self):
         try:
+            nv, h = self._nvml_handle()
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            pass
+        try:
+            self.source = "nvidia-smi"
             self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
@@ -94,24 +129,27 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=3)
             except Exception:
                 self.proc.kill()
+        elif self.t:
+            self.t.join(timeout=1)
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
+        sm, mx, reasons = list(self.sm), list(self.mx), set(self.reasons)
+        sm += [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx += [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         for r in self.rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -258,7 +296,11 @@ def main():
     barrier()
     c0 = r.counters()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    with ClockSampler(local, uuid) as clk:
         barrier()
         ev0.record()
         for _ in range(args.steps):
@@ -341,10 +383,14 @@ def main():
             "gpu_launches": int(launches),
             "stage_ms": stage,
             "tight_bvh": {"wide_nodes": tight_nodes, "split_triangles": tight_always, "per_ray": per_ray},
-            "roofline": {"bound": "hbm", "kernel": "k_extend+k_shadow (BVH traversal)", "achieved": round(achieved, 2) if achieved else None,
+            "roofline": {"bound": "hbm", "kernel": "k_traverse (BVH traversal of the extend and shadow rays)", "achieved": round(achieved, 2) if achieved else None,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
                          "traffic": traffic, "algorithmic_bytes_per_launch": round((rays / world) * a_ray / max(n_trav_launches, 1), 0),
                          "bytes_per_ray": round(a_ray, 1), "launches": n_trav_launches, "physical_limiter_ncu": physical,
+                         "physical": None if not traffic else {
+                             "dram_gbs": round(traffic * n_trav_launches / (trav_ms * 1e-3) / 1e9, 1),
+                             "frac_of_peak": round(traffic * n_trav_launches / (trav_ms * 1e-3) / 1e9 / peak, 4),
+                             "what": "ncu DRAM bytes per launch x launches / live CUDA-event traversal time"},
                          "note": "algorithmic bytes follow the REFERENCE traversal (no distance culling, SURVEY.md 8(d)); the scene is "
                                  "cache resident and this path culls, so frac can exceed 1 - ncu shows the kernel is issue-bound, not HBM-bound",
                          "reference_traversal": {k: round(od[k], 3) for k in ("rays_per_sample", "nodes_per_ray", "tris_per_ray")}},
