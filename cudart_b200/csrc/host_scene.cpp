@@ -15,6 +15,8 @@
 #include "host_scene.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -38,11 +40,24 @@ struct BuildNode {
     uint32_t first = 0, count = 0;      // leaf payload
 };
 
+// The tree is defined by the reference's SEQUENTIAL recursion (std::partition / std::nth_element per range, D26), but
+// the two halves of a split touch disjoint ranges of the primitive array and a leaf's triangles end up exactly where
+// the partitions left them (the reference emits the lower half first, so its `orderedTriangles` is the final array
+// order).  Large subtrees are therefore built on their own threads ("parallel host" flavour): same
+// nodes, same order, bit for bit - the node pool is pre-sized and handed out by an atomic counter, and `flatten`
+// lays the nodes out afterwards from the tree structure alone.
 struct Builder {
     const RefTriangle* src;
     std::vector<PrimBox> prims;
-    std::vector<RefTriangle> ordered;
     std::vector<BuildNode> pool;
+    std::atomic<int> next_node{0};
+    // fork only for subtrees of at least this many triangles (CRT_BVH_FORK_MIN overrides it: the tests force forking on
+    // the small golden scenes) in the top levels (at most 16 threads)
+    static uint32_t fork_min() {
+        static const uint32_t v = [] { const char* e = getenv("CRT_BVH_FORK_MIN"); return e ? (uint32_t)std::max(8, atoi(e)) : (1u << 14); }();
+        return v;
+    }
+    static constexpr int kForkDepth = 4;
 
     // "volume as area" (bvh.cpp:334-337)
     static float box_measure(const F3& mn, const F3& mx) {
@@ -70,11 +85,10 @@ struct Builder {
 
     int emit_leaf(int node, uint32_t start, uint32_t end, const F3& mn, const F3& mx) {
         BuildNode& nd = pool[node];
-        nd.first = (uint32_t)ordered.size();
+        nd.first = start;               // == orderedTriangles.size() at this point of the reference's recursion (bvh.cpp:150-152)
         nd.count = end - start;
         nd.mn = mn;
         nd.mx = mx;
-        for (uint32_t i = start; i < end; i++) ordered.push_back(src[prims[i].tri]);
         return node;
     }
 
@@ -84,9 +98,8 @@ struct Builder {
                          [dim](const PrimBox& a, const PrimBox& b) { return axis_of(a.center, dim) < axis_of(b.center, dim); });
     }
 
-    int build(uint32_t start, uint32_t end) {
-        int node = (int)pool.size();
-        pool.emplace_back();
+    int build(uint32_t start, uint32_t end, int depth = 0) {
+        const int node = next_node.fetch_add(1);
         F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX};
         for (uint32_t i = start; i < end; i++) {
             mn = lo3(mn, prims[i].mn);
@@ -143,8 +156,15 @@ struct Builder {
                 median_split(start, mid, end, dim);
             }
         }
-        int lower = build(start, mid);      // built and emitted FIRST (D3) ...
-        int upper = build(mid, end);
+        int lower, upper;
+        if (depth < kForkDepth && n >= fork_min()) {
+            std::thread t([&, this] { lower = build(start, mid, depth + 1); });
+            upper = build(mid, end, depth + 1);
+            t.join();
+        } else {
+            lower = build(start, mid, depth + 1);      // built and emitted FIRST (D3) ...
+            upper = build(mid, end, depth + 1);
+        }
         BuildNode& nd = pool[node];
         nd.child0 = upper;                  // ... but stored second: child 0 is the upper partition
         nd.child1 = lower;
@@ -178,7 +198,6 @@ void build_reference_bvh(RefTriangle* tris, const float* positions, uint32_t n, 
     Builder b;
     b.src = tris;
     b.prims.reserve(n);
-    b.ordered.reserve(n);
     for (uint32_t i = 0; i < n; i++) {            // bvh.cpp:79-96 (boxes from the three vertex positions)
         const float* p = positions + 9 * (size_t)i;
         F3 a{p[0], p[1], p[2]}, c{p[3], p[4], p[5]}, d{p[6], p[7], p[8]};
@@ -191,11 +210,13 @@ void build_reference_bvh(RefTriangle* tris, const float* positions, uint32_t n, 
     }
     nodes_out.clear();
     if (n == 0) return;
-    b.pool.reserve(2 * (size_t)n);
+    b.pool.resize(2 * (size_t)n);
     int root = b.build(0, n);
-    nodes_out.reserve(b.pool.size());
+    nodes_out.reserve((size_t)b.next_node.load());
     b.flatten(root, nodes_out);
-    std::copy(b.ordered.begin(), b.ordered.end(), tris);
+    std::vector<RefTriangle> ordered(n);
+    for (uint32_t i = 0; i < n; i++) ordered[i] = tris[b.prims[i].tri];
+    std::copy(ordered.begin(), ordered.end(), tris);
 }
 
 void build_light_list(RefTriangle* tris, uint32_t n, float* mat_floats, const int32_t* mat_indices, uint32_t n_mats,
@@ -488,16 +509,48 @@ struct TightPrim { uint32_t first, count; F3 mn, mx, c; };     // members[first 
 struct TightBuilder {
     std::vector<TightPrim> prims;
     std::vector<uint32_t> members;               // triangle indices, grouped per primitive
-    std::vector<RefNode> out;
+    std::vector<RefNode> out;                    // after finish(): pre-order layout (first child = index + 1, offset = second)
     std::vector<uint32_t> order;                 // tight slot -> original triangle index
+    // Large subtrees are built on their own threads (disjoint primitive ranges): nodes come from a pre-sized pool
+    // through an atomic counter, a leaf's slots are known from the weight in front of it, and finish() lays the pool
+    // out in pre-order afterwards.  The result does not depend on the number of threads.
+    std::vector<RefNode> pool;
+    std::vector<int32_t> first_child;
+    std::atomic<uint32_t> next_node{0};
+
+    void run() {
+        uint32_t total = 0;
+        for (const TightPrim& p : prims) total += p.count;
+        pool.assign(2 * prims.size() + 2, RefNode{});
+        first_child.assign(pool.size(), -1);
+        order.assign(total, 0u);
+        next_node = 0;
+        const uint32_t root = build(0, (uint32_t)prims.size(), 0, 0);
+        out.clear();
+        out.reserve(next_node.load());
+        std::vector<std::pair<uint32_t, int32_t>> todo;          // (pool node, index of the parent waiting for its second child)
+        todo.push_back({root, -1});
+        while (!todo.empty()) {
+            const auto [k, parent] = todo.back();
+            todo.pop_back();
+            const uint32_t my = (uint32_t)out.size();
+            out.push_back(pool[k]);
+            if (parent >= 0) out[(size_t)parent].offset = (int32_t)my;
+            if (pool[k].nTris <= 0) {
+                todo.push_back({(uint32_t)pool[k].offset, (int32_t)my});     // second child: after the whole first subtree
+                todo.push_back({(uint32_t)first_child[k], -1});              // first child: next in pre-order
+            }
+        }
+        pool.clear(); pool.shrink_to_fit();
+        first_child.clear(); first_child.shrink_to_fit();
+    }
 
     static double area(const F3& mn, const F3& mx) {
         const double dx = std::max(0.0, (double)mx.x - mn.x), dy = std::max(0.0, (double)mx.y - mn.y), dz = std::max(0.0, (double)mx.z - mn.z);
         return dx * dy + dy * dz + dz * dx;
     }
-    uint32_t build(uint32_t lo, uint32_t hi) {
-        const uint32_t my = (uint32_t)out.size();
-        out.emplace_back();
+    uint32_t build(uint32_t lo, uint32_t hi, uint32_t slot_base, int depth) {
+        const uint32_t my = next_node.fetch_add(1);
         F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}, cmn = mn, cmx = mx;
         uint32_t weight = 0;
         for (uint32_t i = lo; i < hi; i++) {
@@ -507,13 +560,14 @@ struct TightBuilder {
         }
         const uint32_t n = hi - lo;
         auto make_leaf = [&]() {
-            RefNode& nd = out[my];
+            RefNode& nd = pool[my];
             std::memset(&nd, 0, sizeof nd);
             nd.mn = mn; nd.mx = mx;
-            nd.offset = (int32_t)order.size();
+            nd.offset = (int32_t)slot_base;
             nd.nTris = (int16_t)weight;
+            uint32_t slot = slot_base;
             for (uint32_t i = lo; i < hi; i++)
-                for (uint32_t m = 0; m < prims[i].count; m++) order.push_back(members[prims[i].first + m]);
+                for (uint32_t m = 0; m < prims[i].count; m++) order[slot++] = members[prims[i].first + m];
             return my;
         };
         // SAH with the traversal cost measured on B200: one wide-node visit costs about as much as eight triangle
@@ -569,15 +623,38 @@ struct TightBuilder {
             if (leaf_ok && weight <= kMaxLeaf) return make_leaf();
             mid = (lo + hi) / 2;
         }
-        build(lo, mid);
-        const uint32_t second = build(mid, hi);
-        RefNode& nd = out[my];
+        uint32_t left_weight = 0;
+        for (uint32_t i = lo; i < mid; i++) left_weight += prims[i].count;
+        uint32_t first, second;
+        if (depth < 4 && n >= (1u << 14)) {
+            std::thread t([&, this] { first = build(lo, mid, slot_base, depth + 1); });
+            second = build(mid, hi, slot_base + left_weight, depth + 1);
+            t.join();
+        } else {
+            first = build(lo, mid, slot_base, depth + 1);
+            second = build(mid, hi, slot_base + left_weight, depth + 1);
+        }
+        RefNode& nd = pool[my];
         std::memset(&nd, 0, sizeof nd);
         nd.mn = mn; nd.mx = mx;
         nd.offset = (int32_t)second;
+        first_child[my] = (int32_t)first;
         return my;
     }
 };
+// fn(begin, end) over [0, n) in contiguous chunks on the host's threads (the chunks write disjoint outputs)
+template <class F>
+void parallel_for(uint32_t n, F fn) {
+    const uint32_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const uint32_t parts = n < (1u << 15) ? 1u : hw;
+    if (parts == 1) { fn(0u, n); return; }
+    std::vector<std::thread> th;
+    for (uint32_t p = 0; p < parts; p++) {
+        const uint32_t b = (uint32_t)((uint64_t)n * p / parts), e = (uint32_t)((uint64_t)n * (p + 1) / parts);
+        th.emplace_back([=, &fn] { fn(b, e); });
+    }
+    for (auto& t : th) t.join();
+}
 inline float round_down(double v) { float f = (float)v; return (double)f > v ? std::nextafterf(f, -INFINITY) : f; }
 inline float round_up(double v) { float f = (float)v; return (double)f < v ? std::nextafterf(f, INFINITY) : f; }
 
@@ -644,6 +721,12 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
         bd.members.insert(bd.members.end(), m.begin(), m.end());
         bd.prims.push_back(pr);
     };
+    // the per-triangle bound is the expensive part (double precision, square roots): all host threads
+    std::vector<F3> infl_mn(n_tris), infl_mx(n_tris);
+    std::vector<uint8_t> infl_ok(n_tris);
+    parallel_for(n_tris, [&](uint32_t b, uint32_t e) {
+        for (uint32_t i = b; i < e; i++) infl_ok[i] = inflated_box(tris[i], region_lo, region_hi, infl_mn[i], infl_mx[i]) ? 1 : 0;
+    });
     std::vector<uint32_t> bounded, unbounded, one(1);
     std::vector<F3> bmn, bmx;
     for (uint32_t k = 0; k < n_ref_nodes; k++) {
@@ -662,8 +745,8 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
             const uint32_t idx = (uint32_t)lf.offset + i;
             if (leaf_of[idx] != 0xffffffffu) continue;                       // overlapping leaves: first owner wins
             leaf_of[idx] = k;
-            F3 mn, mx;
-            if (inflated_box(tris[idx], region_lo, region_hi, mn, mx)) {
+            const F3 mn = infl_mn[idx], mx = infl_mx[idx];
+            if (infl_ok[idx]) {
                 bounded.push_back(idx); bmn.push_back(mn); bmx.push_back(mx);
                 split_cost += TightBuilder::area(mn, mx);
             } else {
@@ -697,8 +780,7 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
     std::vector<RefNode>& nodes = out.nodes;
     std::vector<uint32_t> order;
     auto append = [&](TightBuilder& bd) {          // build bd's tree and splice it behind `nodes` / `order`
-        bd.out.reserve(2 * bd.prims.size());
-        bd.build(0, (uint32_t)bd.prims.size());
+        bd.run();
         const uint32_t nbase = (uint32_t)nodes.size(), obase = (uint32_t)order.size();
         for (RefNode nd : bd.out) {
             if (nd.nTris > 0) nd.offset += (int32_t)obase; else nd.offset += (int32_t)nbase;
@@ -729,6 +811,7 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
         r.v1[0] = t.v1.x; r.v1[1] = t.v1.y; r.v1[2] = t.v1.z;
         r.e1[0] = t.e1.x; r.e1[1] = t.e1.y; r.e1[2] = t.e1.z;
         r.e2[0] = t.e2.x; r.e2[1] = t.e2.y; r.e2[2] = t.e2.z;
+        r.materialId = t.materialId;
         r.origIdx = i;
         const RefNode& lf = ref_nodes[leaf_of[i]];
         r.leafFirst = (uint32_t)lf.offset;
@@ -769,6 +852,7 @@ void make_tri_records(const RefTriangle* tris, uint32_t n, const RefNode* nodes,
         a.e1[0] = t.e1.x; a.e1[1] = t.e1.y; a.e1[2] = t.e1.z;
         a.e2[0] = t.e2.x; a.e2[1] = t.e2.y; a.e2[2] = t.e2.z;
         a.materialId = t.materialId;
+        a.index = i;
         a.leafFirst = 0;
         TriShade& s = shade[i];
         std::memset(&s, 0, sizeof s);

@@ -54,8 +54,9 @@ constexpr uint32_t kMaxTris = 1u << 26;
 // leaf reference: bit31 set | (count-1) << 26 | first triangle
 inline int32_t leaf_ref(uint32_t first, uint32_t count) { return (int32_t)(0x80000000u | ((count - 1) << 26) | first); }
 
-// Intersection record, 48 B = 3 x float4: (v1, leafFirst bits) (e1, materialId bits) (e2, 0)
-struct TriIsect { float v1[3]; uint32_t leafFirst; float e1[3]; uint32_t materialId; float e2[3]; uint32_t pad; };
+// Intersection record, 48 B = 3 x float4: (v1, triangle index) (e1, leafFirst) (e2, materialId) - the same first three
+// vectors as a TightRecord, so the traversal reads either through one (base, stride) pair per ray
+struct TriIsect { float v1[3]; uint32_t index; float e1[3]; uint32_t leafFirst; float e2[3]; uint32_t materialId; };
 static_assert(sizeof(TriIsect) == 48, "intersection record");
 // Shading record, 80 B = 5 x float4: (n1, area) (n2, materialId bits) (n3, 0) (uv1, uv2) (uv3, 0, 0)
 struct TriShade {
@@ -101,7 +102,7 @@ uint32_t pack_cull_bound(CullBound b);
 struct TightRecord {            // 80 B = 5 x float4
     float v1[3]; uint32_t origIdx;          // index in the reference's (BVH-ordered) triangle array = what hits report
     float e1[3]; uint32_t leafFirst;        // firstTriOffset of the reference leaf (tie key)
-    float e2[3]; uint32_t pad0;
+    float e2[3]; uint32_t materialId;
     float gateLo[3]; float gateHiX;         // the reference leaf's exact box
     float gateHiY, gateHiZ; uint32_t pad1[2];
 };

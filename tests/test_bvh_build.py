@@ -97,3 +97,29 @@ def test_large_terrain_matches_reference_when_it_is_present(tmp_path):
     assert all(np.array_equal(mine.nodes[k], ref.nodes[k]) for k in mine.nodes.dtype.names)
     assert same_triangles(mine.tris, ref.tris)
     assert np.array_equal(mine.light_indices, ref.light_indices) and mine.camera.tobytes() == ref.camera.tobytes()
+
+
+def test_threaded_bvh_build_is_the_sequential_tree():
+    """Subtrees of >= 16 384 triangles are built on their own threads (parallel-host flavour).  Force the
+    fork threshold down to 8 triangles in a fresh process and require the golden (reference) tree on every fixture."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from conftest import SCENES, GOLDEN\n"
+        "from cudart_b200 import scenebuild, load_crts\n"
+        "from cudart_b200.scenefile import TRIANGLE_DTYPE\n"
+        "import os\n"
+        "for name in SCENES:\n"
+        "    fs = load_crts(os.path.join(GOLDEN, name + '.crts.gz'))\n"
+        "    z = np.load(os.path.join(GOLDEN, name + '.golden.npz'))\n"
+        "    tris, nodes = scenebuild.build_bvh(z['pretris'].view(TRIANGLE_DTYPE), z['positions'])\n"
+        "    assert nodes.shape[0] == fs.n_nodes, name\n"
+        "    assert all(np.array_equal(nodes[k], fs.nodes[k]) for k in nodes.dtype.names), name\n"
+        "    assert all(np.array_equal(tris[k].view(np.uint32), fs.tris[k].view(np.uint32)) for k in tris.dtype.names if k != 'triId'), name\n"
+        "print('ok')\n" % (root, os.path.join(root, "tests")))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CRT_BVH_FORK_MIN="8"), capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
