@@ -743,7 +743,9 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
         double split_cost = 0;
         for (uint32_t i = 0; i < (uint32_t)(uint16_t)lf.nTris && (uint32_t)lf.offset + i < n_tris; i++) {
             const uint32_t idx = (uint32_t)lf.offset + i;
-            if (leaf_of[idx] != 0xffffffffu) continue;                       // overlapping leaves: first owner wins
+            // a triangle claimed by two leaves (not a tree the reference builds) is reachable through either box: the gate
+            // could not say which, so such input keeps the reference-leaf tree only
+            if (leaf_of[idx] != 0xffffffffu) { out = TightBvh(); return; }
             leaf_of[idx] = k;
             const F3 mn = infl_mn[idx], mx = infl_mx[idx];
             if (infl_ok[idx]) {
