@@ -59,6 +59,60 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Two independent 64-bit multiply-xorshift hashes over 8-byte words, four lanes each for instruction-level parallelism
+// (~8 bytes per cycle: 160 MB of triangles and nodes in ~10 ms).  Not cryptographic: it only answers "is this the
+// geometry this context flattened last time?" for crt_update_scene.
+struct Fingerprint {
+    uint64_t a = 0, b = 0;
+    bool operator==(const Fingerprint& o) const { return a == o.a && b == o.b; }
+};
+void fingerprint_mix(Fingerprint& fp, const void* data, size_t bytes) {
+    const unsigned char* p = (const unsigned char*)data;
+    uint64_t ha[4] = {fp.a ^ bytes, 0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull};
+    uint64_t hb[4] = {fp.b + bytes, 0x082EFA98EC4E6C89ull, 0x452821E638D01377ull, 0xBE5466CF34E90C6Cull};
+    size_t i = 0;
+    for (; i + 32 <= bytes; i += 32) {
+        uint64_t w[4];
+        memcpy(w, p + i, 32);
+        for (int k = 0; k < 4; k++) {
+            ha[k] = (ha[k] ^ w[k]) * 0x9E3779B97F4A7C15ull; ha[k] ^= ha[k] >> 29;
+            hb[k] = (hb[k] + w[k]) * 0xC2B2AE3D27D4EB4Full; hb[k] ^= hb[k] >> 31;
+        }
+    }
+    uint64_t tail[4] = {0, 0, 0, 0};
+    memcpy(tail, p + i, bytes - i);
+    for (int k = 0; k < 4; k++) {
+        ha[k] = (ha[k] ^ tail[k]) * 0x9E3779B97F4A7C15ull; ha[k] ^= ha[k] >> 29;
+        hb[k] = (hb[k] + tail[k]) * 0xC2B2AE3D27D4EB4Full; hb[k] ^= hb[k] >> 31;
+    }
+    fp.a = ((ha[0] * 3 + ha[1]) * 5 + ha[2]) * 7 + ha[3];
+    fp.b = ((hb[0] * 11 + hb[1]) * 13 + hb[2]) * 17 + hb[3];
+}
+
+// What upload_scene derives from the caller's triangles and BVH nodes on the host.  Kept per context so that
+// crt_update_scene with unchanged geometry (a new camera direction, new materials, the same frame again) re-uploads
+// these arrays without rebuilding them: the 999 700-triangle terrain takes 0.9 s to flatten and 15 ms to re-upload.
+struct HostSceneCache {
+    bool valid = false;
+    Fingerprint fp;
+    std::vector<WideNode> wide;             // tight tree (if any) followed by the reference-leaf tree
+    std::vector<TriIsect> isect;
+    std::vector<TriShade> shade;
+    std::vector<TightRecord> tight_records;
+    std::vector<float4> light_boxes;
+    WideStats wide_stats{};
+    uint32_t n_tight_wide = 0, tight_split = 0, n_front = 0;
+    F3 region_lo{FLT_MAX, FLT_MAX, FLT_MAX}, region_hi{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool coords_bounded = false;
+    std::vector<const void*> pinned;        // cudaHostRegister'ed staging arrays (async copies at full PCIe rate)
+    void unpin() { for (const void* q : pinned) cudaHostUnregister(const_cast<void*>(q)); pinned.clear(); }
+    template <class V> void pin(const V& v) {
+        if (v.size() * sizeof(v[0]) < (1u << 20)) return;                  // small arrays: not worth a registration
+        if (cudaHostRegister((void*)v.data(), v.size() * sizeof(v[0]), cudaHostRegisterDefault) == cudaSuccess) pinned.push_back(v.data());
+        else cudaGetLastError();                                           // pageable copy still works
+    }
+};
+
 }  // namespace
 
 struct crt_ctx {
@@ -73,6 +127,8 @@ struct crt_ctx {
     DTiling tl{};
     DWave wv{};
     WideStats wide_stats{};
+    HostSceneCache host_scene;
+    uint64_t scene_rebuilds = 0, scene_uploads = 0, scene_upload_bytes = 0;
     // scene
     DevBuf<float4> wide, tri_isect, tri_shade, tri_tight, mats, light_boxes;
     uint32_t tight_split = 0, tight_nodes = 0;
@@ -96,15 +152,19 @@ struct crt_ctx {
 
 namespace {
 
+thread_local uint64_t g_uploaded_bytes = 0;            // host -> device bytes of the upload_scene call in progress
+
 template <typename T>
 int upload(DevBuf<T>& b, const void* src, size_t count, cudaStream_t s) {
     CU(b.alloc(count));
     if (count) CU(cudaMemcpyAsync(b.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    g_uploaded_bytes += count * sizeof(T);
     return CRT_OK;
 }
 
 void free_all(crt_ctx* c) {
     cudaSetDevice(c->device);
+    c->host_scene.unpin();
     c->wide.release(); c->tri_isect.release(); c->tri_shade.release(); c->mats.release();
     c->lights.release(); c->light_boxes.release(); c->tex_dims.release(); c->tex_offsets.release(); c->tex_data.release();
     for (int i = 0; i < 2; i++) { c->rq_o[i].release(); c->rq_d[i].release(); c->rq_path[i].release(); }
@@ -141,27 +201,47 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
                                      "light list in that case, SURVEY.md D13)");
     for (uint32_t k = 0; k < s->n_lights; k++)
         if (s->light_indices[k] >= s->n_tris) return (fail(CRT_ERR_INVALID, "scene: light index out of range"));
+    // Fingerprint of everything the derived arrays depend on: geometry, BVH, lights, the flags that pick the trees, and
+    // the camera position / aperture (the tight tree's region of valid ray origins contains the eye).
+    const RefCamera* cam_in = (const RefCamera*)s->camera;
+    Fingerprint fp;
+    {
+        const uint32_t hdr[6] = {s->n_tris, s->n_nodes, s->n_lights,
+                                 c->flags & (CRT_FLAG_REFERENCE_TOPOLOGY | CRT_FLAG_NO_TIGHT_BVH | CRT_FLAG_EXACT_VISIT | CRT_FLAG_TIGHT_BVH),
+                                 (uint32_t)sizeof(RefTriangle), (uint32_t)sizeof(RefNode)};
+        fingerprint_mix(fp, hdr, sizeof hdr);
+        const float eye[4] = {cam_in->eye.x, cam_in->eye.y, cam_in->eye.z, cam_in->apertureWidth};
+        fingerprint_mix(fp, eye, sizeof eye);
+        fingerprint_mix(fp, s->light_indices, sizeof(uint32_t) * (size_t)s->n_lights);
+        fingerprint_mix(fp, nodes, sizeof(RefNode) * (size_t)s->n_nodes);
+        fingerprint_mix(fp, tris, sizeof(RefTriangle) * (size_t)s->n_tris);
+    }
+    HostSceneCache& hc = c->host_scene;
+    if (!(hc.valid && hc.fp == fp)) {
+    hc.valid = false;
+    hc.unpin();
     // The reference-leaf tree (re-cluster + 4-ary flatten), the shading records and the tight BVH below are independent
     // host jobs: the first two run on their own threads while this one builds the tight tree (large scenes: 1.8 s -> 0.9 s
     // for 999 700 triangles).
-    std::vector<WideNode> wide;
+    std::vector<WideNode>& wide = hc.wide;
+    wide.clear();
     std::vector<RefNode> ref_tree;          // the binary tree behind `wide`, for the cost comparison below
     std::thread ref_job([&] {
         std::vector<RefNode> clustered;
         if (!(c->flags & CRT_FLAG_REFERENCE_TOPOLOGY)) recluster_leaves(nodes, s->n_nodes, clustered);
-        c->wide_stats = clustered.empty() ? flatten_wide(nodes, s->n_nodes, tris, s->n_tris, wide)
+        hc.wide_stats = clustered.empty() ? flatten_wide(nodes, s->n_nodes, tris, s->n_tris, wide)
                                           : flatten_wide(clustered.data(), (uint32_t)clustered.size(), tris, s->n_tris, wide);
         if (clustered.empty()) ref_tree.assign(nodes, nodes + s->n_nodes); else ref_tree.swap(clustered);
     });
-    std::vector<TriIsect> isect;
-    std::vector<TriShade> shade;
+    std::vector<TriIsect>& isect = hc.isect;
+    std::vector<TriShade>& shade = hc.shade;
     std::thread rec_job([&] { make_tri_records(tris, s->n_tris, nodes, s->n_nodes, isect, shade); });
     struct Joiner { std::thread &a, &b; ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); } } joiner{ref_job, rec_job};
     // ---- tight per-triangle BVH in front of the reference-leaf tree (host_scene.h) ----
     TightBvh tight;
     F3 region_lo{FLT_MAX, FLT_MAX, FLT_MAX}, region_hi{-FLT_MAX, -FLT_MAX, -FLT_MAX};
     uint32_t n_tight_wide = 0;
-    c->tight_split = c->tight_nodes = 0;
+    hc.tight_split = 0;
     if (!(c->flags & (CRT_FLAG_NO_TIGHT_BVH | CRT_FLAG_EXACT_VISIT))) {
         // region: every vertex and the camera, grown by 5 % of the diagonal (hit points on the scene's hull round outwards)
         auto grow = [&](double x, double y, double z) {
@@ -197,7 +277,7 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
         }
     }
     if (ref_job.joinable()) ref_job.join();
-    if (3 * c->wide_stats.depth + 4 > 64) return (fail(CRT_ERR_LIMIT, "scene: wide BVH depth %u exceeds the traversal stack", c->wide_stats.depth));
+    if (3 * hc.wide_stats.depth + 4 > 64) return (fail(CRT_ERR_LIMIT, "scene: wide BVH depth %u exceeds the traversal stack", hc.wide_stats.depth));
     if (!tight.nodes.empty()) {
         std::vector<WideNode> tw;
         const WideStats ts = flatten_wide(tight.nodes.data(), (uint32_t)tight.nodes.size(), tight.tris.data(), s->n_tris, tw);
@@ -210,11 +290,44 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
                     if (w.child[k] >= 0 && w.child[k] != kEmptyChild) w.child[k] += (int32_t)n_tight_wide;
             tw.insert(tw.end(), wide.begin(), wide.end());
             wide.swap(tw);
-            c->tight_split = tight.n_split;
-            c->tight_nodes = n_tight_wide;
+            hc.tight_split = tight.n_split;
         }
     }
     rec_job.join();
+    hc.n_front = (uint32_t)(n_tight_wide ? n_tight_wide : wide.size());    // the tree the render path's rays walk
+    hc.n_tight_wide = n_tight_wide;
+    hc.tight_records.swap(tight.records);
+    if (!n_tight_wide) hc.tight_records.clear();
+    hc.region_lo = region_lo; hc.region_hi = region_hi;
+    {   // the reference leaf holding each light triangle
+        hc.light_boxes.assign(2 * (size_t)s->n_lights, make_float4(0.f, 0.f, 0.f, 0.f));
+        std::vector<uint32_t> leaf_of_first(s->n_tris, 0xffffffffu);
+        for (uint32_t j = 0; j < s->n_nodes; j++)
+            if (nodes[j].nTris > 0) leaf_of_first[(uint32_t)nodes[j].offset] = j;
+        for (uint32_t k = 0; k < s->n_lights; k++) {
+            const uint32_t j = leaf_of_first[isect[s->light_indices[k]].leafFirst];
+            if (j == 0xffffffffu) return (fail(CRT_ERR_INVALID, "scene: light %u is in no BVH leaf", k));
+            hc.light_boxes[2 * k] = make_float4(nodes[j].mn.x, nodes[j].mn.y, nodes[j].mn.z, 0.f);
+            hc.light_boxes[2 * k + 1] = make_float4(nodes[j].mx.x, nodes[j].mx.y, nodes[j].mx.z, 0.f);
+        }
+    }
+    {
+        bool bounded = true;
+        for (uint32_t k = 0; k < s->n_nodes && bounded; k++) {
+            const float v[6] = {nodes[k].mn.x, nodes[k].mn.y, nodes[k].mn.z, nodes[k].mx.x, nodes[k].mx.y, nodes[k].mx.z};
+            for (float f : v) bounded = bounded && std::isfinite(f) && std::fabs(f) < 1e8f;
+        }
+        hc.coords_bounded = bounded;
+    }
+    hc.pin(hc.wide); hc.pin(hc.isect); hc.pin(hc.shade); hc.pin(hc.tight_records);
+    hc.fp = fp;
+    hc.valid = true;
+    c->scene_rebuilds++;
+    }
+    c->wide_stats = hc.wide_stats;
+    c->tight_split = hc.tight_split;
+    c->tight_nodes = hc.n_tight_wide;
+    const uint32_t n_tight_wide = hc.n_tight_wide;
     for (uint32_t i = 0; i < s->n_tris; i++)
         if (tris[i].materialId >= std::max(s->n_mats, 1u)) return (fail(CRT_ERR_INVALID, "scene: triangle %u has material %u of %u", i, tris[i].materialId, s->n_mats));
     std::vector<float4> mats(4 * (size_t)std::max(s->n_mats, 1u));
@@ -230,27 +343,16 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
         mats[4 * m + 3] = make_float4(f[9], f[10], f[11], 0.f);
     }
     int rc;
+    g_uploaded_bytes = 0;
 #define UP(buf, src, count) if ((rc = upload(c->buf, src, count, c->stream)) != CRT_OK) return rc
-    UP(wide, wide.data(), wide.size() * 8);
-    UP(tri_isect, isect.data(), isect.size() * 3);
-    UP(tri_shade, shade.data(), shade.size() * 5);
-    if (n_tight_wide) { UP(tri_tight, tight.records.data(), tight.records.size() * 5); }
+    UP(wide, hc.wide.data(), hc.wide.size() * 8);
+    UP(tri_isect, hc.isect.data(), hc.isect.size() * 3);
+    UP(tri_shade, hc.shade.data(), hc.shade.size() * 5);
+    if (n_tight_wide) { UP(tri_tight, hc.tight_records.data(), hc.tight_records.size() * 5); }
     else c->tri_tight.release();
     UP(mats, mats.data(), mats.size());
     UP(lights, s->light_indices, s->n_lights);
-    std::vector<float4> lboxes(2 * (size_t)s->n_lights);
-    {   // the reference leaf holding each light triangle
-        std::vector<uint32_t> leaf_of_first(s->n_tris, 0xffffffffu);
-        for (uint32_t j = 0; j < s->n_nodes; j++)
-            if (nodes[j].nTris > 0) leaf_of_first[(uint32_t)nodes[j].offset] = j;
-        for (uint32_t k = 0; k < s->n_lights; k++) {
-            const uint32_t j = leaf_of_first[isect[s->light_indices[k]].leafFirst];
-            if (j == 0xffffffffu) return (fail(CRT_ERR_INVALID, "scene: light %u is in no BVH leaf", k));
-            lboxes[2 * k] = make_float4(nodes[j].mn.x, nodes[j].mn.y, nodes[j].mn.z, 0.f);
-            lboxes[2 * k + 1] = make_float4(nodes[j].mx.x, nodes[j].mx.y, nodes[j].mx.z, 0.f);
-        }
-    }
-    UP(light_boxes, lboxes.data(), lboxes.size());
+    UP(light_boxes, hc.light_boxes.data(), hc.light_boxes.size());
     UP(tex_dims, s->tex_dims, 2 * (size_t)s->n_tex);
     UP(tex_offsets, s->tex_offsets, s->n_tex ? s->n_tex + 1 : 0);
     UP(tex_data, s->tex_data, 3 * (size_t)s->tex_texels);
@@ -261,6 +363,8 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     }
     UP(gamma_lut, lut, 256);
 #undef UP
+    c->scene_uploads++;
+    c->scene_upload_bytes = g_uploaded_bytes;
     DScene& sc = c->sc;
     sc.wide = c->wide.p; sc.tri_isect = c->tri_isect.p; sc.tri_shade = c->tri_shade.p; sc.mats = c->mats.p;
     sc.lights = c->lights.p; sc.light_boxes = c->light_boxes.p; sc.tex_data = c->tex_data.p; sc.tex_dims = c->tex_dims.p; sc.tex_offsets = c->tex_offsets.p;
@@ -269,26 +373,19 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     // when only the top fits (monkeys: 288 of 1058 nodes) the mixed smem/global fetch diverges and costs 3.7 %.
     // Policy: stage iff the whole tree fits, unless forced either way.
     sc.n_smem_nodes = 0;
-    const size_t n_front = n_tight_wide ? n_tight_wide : wide.size();      // the tree the render path's rays walk
+    const size_t n_front = hc.n_front;                                     // the tree the render path's rays walk
     if (!(c->flags & CRT_FLAG_NO_SMEM_NODES) && (n_front <= kMaxSmemNodes || (c->flags & CRT_FLAG_SMEM_TOP_LEVELS)))
         sc.n_smem_nodes = std::min<uint32_t>((uint32_t)n_front, kMaxSmemNodes);
     sc.tri_tight = n_tight_wide ? c->tri_tight.p : nullptr;
     sc.ref_root = n_tight_wide;
-    sc.region_lo[0] = region_lo.x; sc.region_lo[1] = region_lo.y; sc.region_lo[2] = region_lo.z;
-    sc.region_hi[0] = region_hi.x; sc.region_hi[1] = region_hi.y; sc.region_hi[2] = region_hi.z;
-    sc.n_wide = (uint32_t)wide.size(); sc.n_tris = s->n_tris; sc.n_mats = s->n_mats; sc.n_lights = s->n_lights;
+    sc.region_lo[0] = hc.region_lo.x; sc.region_lo[1] = hc.region_lo.y; sc.region_lo[2] = hc.region_lo.z;
+    sc.region_hi[0] = hc.region_hi.x; sc.region_hi[1] = hc.region_hi.y; sc.region_hi[2] = hc.region_hi.z;
+    sc.n_wide = (uint32_t)hc.wide.size(); sc.n_tris = s->n_tris; sc.n_mats = s->n_mats; sc.n_lights = s->n_lights;
     sc.n_tex = s->n_tex; sc.tex_texels = s->tex_texels; sc.lights_area = s->lights_area;
     memcpy(&sc.cam, s->camera, sizeof(RefCamera));
     sc.cam.xpixels = (int32_t)W;
     sc.cam.ypixels = (int32_t)H;
-    {
-        bool bounded = true;
-        for (uint32_t k = 0; k < s->n_nodes && bounded; k++) {
-            const float v[6] = {nodes[k].mn.x, nodes[k].mn.y, nodes[k].mn.z, nodes[k].mx.x, nodes[k].mx.y, nodes[k].mx.z};
-            for (float f : v) bounded = bounded && std::isfinite(f) && std::fabs(f) < 1e8f;
-        }
-        sc.coords_bounded = bounded ? 1 : 0;
-    }
+    sc.coords_bounded = hc.coords_bounded ? 1 : 0;
 
     return CRT_OK;
 }
@@ -644,6 +741,31 @@ int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t
         if (!tb.nodes.empty()) flatten_wide(tb.nodes.data(), (uint32_t)tb.nodes.size(), tb.tris.data(), n_tris, tw);
         *n_wide_out = (uint32_t)tw.size();
     }
+    return CRT_OK;
+}
+
+int crt_selftest_reciprocal(crt_ctx* c, uint64_t* n_checked_out, uint64_t* n_mismatch_out) {
+    if (!c) return fail(CRT_ERR_INVALID, "crt_selftest_reciprocal: null ctx");
+    CU(cudaSetDevice(c->device));
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    unsigned long long h[2] = {0, 0};
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof h, c->stream);
+    if (e == cudaSuccess) { launch_selftest_rcp(d, c->cfg); c->launches++; e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(CRT_ERR_CUDA, "crt_selftest_reciprocal: %s", cudaGetErrorString(e));
+    if (n_checked_out) *n_checked_out = h[0];
+    if (n_mismatch_out) *n_mismatch_out = h[1];
+    return CRT_OK;
+}
+
+int crt_scene_info(const crt_ctx* c, uint64_t* host_rebuilds_out, uint64_t* uploads_out, uint64_t* last_upload_bytes_out) {
+    if (!c) return fail(CRT_ERR_INVALID, "crt_scene_info: null ctx");
+    if (host_rebuilds_out) *host_rebuilds_out = c->scene_rebuilds;
+    if (uploads_out) *uploads_out = c->scene_uploads;
+    if (last_upload_bytes_out) *last_upload_bytes_out = c->scene_upload_bytes;
     return CRT_OK;
 }
 

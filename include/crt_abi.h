@@ -117,8 +117,13 @@ int crt_resolve_f32(crt_ctx* ctx, float* dst);
 int crt_read_accum(crt_ctx* ctx, float* dst);
 int crt_reset(crt_ctx* ctx);                                  /* zero accumulator and sample count */
 /* Replace the scene of a live context (next frame of an animation: new geometry / camera / materials), keeping the
- * image size, sharding and all device buffers; copies host -> device like crt_create and resets the accumulator. */
+ * image size, sharding and all device buffers; copies host -> device like crt_create and resets the accumulator.
+ * The arrays derived on the host (4-ary trees, triangle records) are kept per context and only rebuilt when the
+ * triangles, BVH nodes, light list or camera position differ from the previous call; they are uploaded every call. */
 int crt_update_scene(crt_ctx* ctx, const crt_scene_desc* scene);
+/* How often this context rebuilt its derived host arrays, how often it uploaded a scene, and the host -> device bytes
+ * of the last upload. */
+int crt_scene_info(const crt_ctx* ctx, uint64_t* host_rebuilds_out, uint64_t* uploads_out, uint64_t* last_upload_bytes_out);
 int crt_get_counters(crt_ctx* ctx, crt_counters* out);
 
 /* ---- bit-exact test entry: closest hit of the reference traversal (renderer.cu:283-330) -------- */
@@ -158,6 +163,10 @@ int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t
                   uint32_t* n_split_out, uint32_t* n_tight_nodes_out, uint32_t* n_wide_out, double* sah_out /* 4 doubles or null */);
 /* Whether this context's render path walks the tight BVH: its wide-node count (0 = off) and individually boxed triangles. */
 int crt_tight_info(const crt_ctx* ctx, uint32_t* n_tight_wide_out, uint32_t* n_split_out);
+/* Device self-test: the traversal's in-range reciprocal (MUFU.RCP + one Newton step) against the IEEE divide the
+ * reference compiles `1.0f / det` to (geometry.cu:45), for every float with 2^-126 <= |x| < 8.5e37.
+ * Returns the number of values checked and how many differed (must be 0). */
+int crt_selftest_reciprocal(crt_ctx* ctx, uint64_t* n_checked_out, uint64_t* n_mismatch_out);
 
 #ifdef __cplusplus
 }

@@ -387,6 +387,64 @@ def test_update_scene_equals_a_fresh_renderer(golden, B200Renderer):
     r.close()
 
 
+def test_update_scene_rebuilds_only_when_the_geometry_changed(golden, B200Renderer):
+    """crt_update_scene keeps the derived host arrays of a context while triangles / BVH / lights / eye are unchanged
+    (they are still uploaded every call), and a one-bit change of the geometry rebuilds them."""
+    import dataclasses
+    fs, _ = golden("cornellSphere")
+    W, H = 64, 48
+    fs = fs.with_resolution(W, H)
+    r = B200Renderer(fs, W, H, 4)
+    assert r.scene_info()[:2] == (1, 1)
+    r.render(4)
+    first = r.accum()
+    r.update_scene(fs)                                        # same bytes: no rebuild, one more upload
+    rebuilds, uploads, nbytes = r.scene_info()
+    assert (rebuilds, uploads) == (1, 2) and nbytes > fs.n_tris * (48 + 80)
+    r.render(4)
+    assert np.array_equal(r.accum(), first)
+    mats = fs.mat_floats.copy()
+    mats[1, 0] = (0.25, 0.5, 0.75)                            # a new material colour alone keeps the trees
+    recol = dataclasses.replace(fs, mat_floats=mats)
+    r.update_scene(recol)
+    assert r.scene_info()[:2] == (1, 3)
+    r.render(4)
+    fresh = B200Renderer(recol, W, H, 4)
+    fresh.render(4)
+    assert np.array_equal(r.accum(), fresh.accum()) and not np.array_equal(r.accum(), first)
+    fresh.close()
+    cam = fs.camera.copy()
+    cam["eye"][0][1] += 0.125                                 # the eye moved: the tight tree's region moves with it
+    moved = dataclasses.replace(fs, camera=cam)
+    r.update_scene(moved)
+    assert r.scene_info()[:2] == (2, 4)
+    r.render(4)
+    fresh = B200Renderer(moved, W, H, 4)
+    fresh.render(4)
+    assert np.array_equal(r.accum(), fresh.accum())
+    fresh.close()
+    tris = fs.tris.copy()
+    tris["v1"][5][0] = np.nextafter(tris["v1"][5][0], np.float32(np.inf))     # one ulp of one vertex
+    nudged = dataclasses.replace(fs, tris=tris)
+    r.update_scene(nudged)
+    assert r.scene_info()[:2] == (3, 5)
+    r.update_scene(fs)                                        # and back
+    assert r.scene_info()[:2] == (4, 6)
+    r.render(4)
+    assert np.array_equal(r.accum(), first)
+    r.close()
+
+
+def test_traversal_reciprocal_equals_the_ieee_divide(golden, B200Renderer):
+    """Moeller-Trumbore's 1/det (geometry.cu:45) is computed by MUFU.RCP + one Newton step inside 2^-126 <= |det| < 8.5e37
+    and by the IEEE divide outside: the short form must equal the divide for EVERY float of its range."""
+    fs, _ = golden("tiny")
+    r = B200Renderer(fs, 16, 16, 1)
+    checked, bad = r.selftest_reciprocal()
+    r.close()
+    assert checked > 4_200_000_000 and bad == 0, (checked, bad)
+
+
 def test_degenerate_image_shapes_and_empty_ranks(golden, B200Renderer):
     """1x1 and odd-sized images, fewer row tiles than ranks (ranks that own nothing), zero samples."""
     fs, _ = golden("cornell")
