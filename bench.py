@@ -325,6 +325,7 @@ def main():
     if args.stats and rays > 0 and world == 1:
         per_ray = {"wide_nodes_per_ray": round((c1["node_visits"] - c0["node_visits"]) / rays, 2),
                    "tri_tests_per_ray": round((c1["tri_tests"] - c0["tri_tests"]) / rays, 2)}
+    lane_stats = r.lane_stats() if args.stats else None
     r.close()
 
     # ---- e2e through the public API with HOST buffers: every step uploads the scene (host -> device), renders
@@ -390,6 +391,7 @@ def main():
             "gpu_launches": int(launches),
             "stage_ms": stage,
             "tight_bvh": {"wide_nodes": tight_nodes, "split_triangles": tight_always, "per_ray": per_ray},
+            "lane_stats": lane_stats,
             "roofline": {"bound": "hbm", "kernel": "k_traverse (BVH traversal of the extend and shadow rays)", "achieved": round(achieved, 2) if achieved else None,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
                          "traffic": traffic, "algorithmic_bytes_per_launch": round((rays / world) * a_ray / max(n_trav_launches, 1), 0),

@@ -761,6 +761,16 @@ int crt_selftest_reciprocal(crt_ctx* c, uint64_t* n_checked_out, uint64_t* n_mis
     return CRT_OK;
 }
 
+int crt_lane_stats(crt_ctx* c, uint64_t out[8]) {
+    if (!c || !out) return fail(CRT_ERR_INVALID, "crt_lane_stats: null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    DStats st;
+    CU(cudaMemcpy(&st, c->stats.p, sizeof st, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; k++) out[k] = st.lanes[k];
+    return CRT_OK;
+}
+
 int crt_scene_info(const crt_ctx* c, uint64_t* host_rebuilds_out, uint64_t* uploads_out, uint64_t* last_upload_bytes_out) {
     if (!c) return fail(CRT_ERR_INVALID, "crt_scene_info: null ctx");
     if (host_rebuilds_out) *host_rebuilds_out = c->scene_rebuilds;

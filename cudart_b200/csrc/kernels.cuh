@@ -49,6 +49,10 @@ struct DCounters {
 };
 struct DStats {                                // running totals (never reset by a wave)
     unsigned long long extend_rays, shadow_rays, node_visits, tri_tests, samples;
+    // CRT_FLAG_STATS: warp-level loop iterations and lane occupancy of the traversal (crt_lane_stats):
+    // [0] node-loop iterations [1] lanes working in them [2] lanes idle (no ray) during them
+    // [3] leaf-loop (triangle) iterations [4] lanes working [5] lanes idle   [6] refills [7] rays fetched by them
+    unsigned long long lanes[8];
 };
 
 // Wavefront state for up to `capacity` paths in flight.  Everything is SoA at 16-byte granularity:

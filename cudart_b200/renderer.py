@@ -128,6 +128,13 @@ class B200Renderer:
         capi.check(self._lib.crt_tight_info(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def lane_stats(self):
+        """stats=True only: dict of warp-level loop iterations and lane occupancy of the traversal kernels."""
+        out = (C.c_uint64 * 8)()
+        capi.check(self._lib.crt_lane_stats(self._h, C.byref(out)))
+        keys = ("node_iters", "node_lanes", "node_idle", "leaf_iters", "leaf_lanes", "leaf_idle", "refills", "refill_rays")
+        return dict(zip(keys, (int(v) for v in out)))
+
     def scene_info(self):
         """(host rebuilds of the derived scene arrays, scene uploads, host->device bytes of the last upload)."""
         a, b, n = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

@@ -163,6 +163,10 @@ int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t
                   uint32_t* n_split_out, uint32_t* n_tight_nodes_out, uint32_t* n_wide_out, double* sah_out /* 4 doubles or null */);
 /* Whether this context's render path walks the tight BVH: its wide-node count (0 = off) and individually boxed triangles. */
 int crt_tight_info(const crt_ctx* ctx, uint32_t* n_tight_wide_out, uint32_t* n_split_out);
+/* With CRT_FLAG_STATS: where the traversal's SIMT lanes go.  out[0..2] = warp-level iterations of the interior-node loop,
+ * lanes that worked in them, lanes that had no ray; out[3..5] = the same for the triangle loop; out[6..7] = queue
+ * refills and the rays they fetched. */
+int crt_lane_stats(crt_ctx* ctx, uint64_t out[8]);
 /* Device self-test: the traversal's in-range reciprocal (MUFU.RCP + one Newton step) against the IEEE divide the
  * reference compiles `1.0f / det` to (geometry.cu:45), for every float with 2^-126 <= |x| < 8.5e37.
  * Returns the number of values checked and how many differed (must be 0). */

@@ -404,7 +404,7 @@ def test_update_scene_rebuilds_only_when_the_geometry_changed(golden, B200Render
     r.render(4)
     assert np.array_equal(r.accum(), first)
     mats = fs.mat_floats.copy()
-    mats[1, 0] = (0.25, 0.5, 0.75)                            # a new material colour alone keeps the trees
+    mats[:, 0] *= np.float32(0.5)                             # new material colours alone keep the trees
     recol = dataclasses.replace(fs, mat_floats=mats)
     r.update_scene(recol)
     assert r.scene_info()[:2] == (1, 3)
