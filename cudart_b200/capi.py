@@ -82,7 +82,6 @@ SYMBOLS = {
     "crt_tight_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "crt_lane_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64 * 8)]),
     "crt_scene_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
-    "crt_selftest_reciprocal": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
 

@@ -744,23 +744,6 @@ int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t
     return CRT_OK;
 }
 
-int crt_selftest_reciprocal(crt_ctx* c, uint64_t* n_checked_out, uint64_t* n_mismatch_out) {
-    if (!c) return fail(CRT_ERR_INVALID, "crt_selftest_reciprocal: null ctx");
-    CU(cudaSetDevice(c->device));
-    unsigned long long* d = nullptr;
-    CU(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
-    unsigned long long h[2] = {0, 0};
-    cudaError_t e = cudaMemsetAsync(d, 0, sizeof h, c->stream);
-    if (e == cudaSuccess) { launch_selftest_rcp(d, c->cfg); c->launches++; e = cudaGetLastError(); }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d);
-    if (e != cudaSuccess) return fail(CRT_ERR_CUDA, "crt_selftest_reciprocal: %s", cudaGetErrorString(e));
-    if (n_checked_out) *n_checked_out = h[0];
-    if (n_mismatch_out) *n_mismatch_out = h[1];
-    return CRT_OK;
-}
-
 int crt_lane_stats(crt_ctx* c, uint64_t out[8]) {
     if (!c || !out) return fail(CRT_ERR_INVALID, "crt_lane_stats: null argument");
     CU(cudaSetDevice(c->device));

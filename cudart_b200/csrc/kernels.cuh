@@ -91,7 +91,4 @@ void launch_trace(const DScene& sc, const float4* rays, uint32_t n, float4* hits
 // Resolve: accum is rank-major (world x padded_pixels float4) when gathered, else this rank's compact buffer.
 void launch_resolve(const DTiling& tl, const float4* accum, bool gathered, uint32_t spp, const uint8_t* gamma_lut,
                     uchar4* rgba_out, float* f32_out, int f32_mode /*0 none,1 mean,2 sum*/, const LaunchCfg& cfg);
-// Device self-test of the traversal's in-range reciprocal: out[0] += values checked, out[1] += mismatches.
-void launch_selftest_rcp(unsigned long long* out, const LaunchCfg& cfg);
-
 }  // namespace crt

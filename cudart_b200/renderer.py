@@ -141,12 +141,6 @@ class B200Renderer:
         capi.check(self._lib.crt_scene_info(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return int(a.value), int(b.value), int(n.value)
 
-    def selftest_reciprocal(self):
-        """(floats checked, mismatches) of the traversal's short reciprocal against the IEEE divide, all 2^32 patterns."""
-        n, bad = C.c_uint64(0), C.c_uint64(0)
-        capi.check(self._lib.crt_selftest_reciprocal(self._h, C.byref(n), C.byref(bad)))
-        return int(n.value), int(bad.value)
-
     def accum_device_ptr(self):
         p, n = C.c_void_p(), C.c_size_t()
         capi.check(self._lib.crt_accum_device_ptr(self._h, C.byref(p), C.byref(n)))

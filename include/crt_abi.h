@@ -167,10 +167,6 @@ int crt_tight_info(const crt_ctx* ctx, uint32_t* n_tight_wide_out, uint32_t* n_s
  * lanes that worked in them, lanes that had no ray; out[3..5] = the same for the triangle loop; out[6..7] = queue
  * refills and the rays they fetched. */
 int crt_lane_stats(crt_ctx* ctx, uint64_t out[8]);
-/* Device self-test: the traversal's in-range reciprocal (MUFU.RCP + one Newton step) against the IEEE divide the
- * reference compiles `1.0f / det` to (geometry.cu:45), for every float with 2^-126 <= |x| < 8.5e37.
- * Returns the number of values checked and how many differed (must be 0). */
-int crt_selftest_reciprocal(crt_ctx* ctx, uint64_t* n_checked_out, uint64_t* n_mismatch_out);
 
 #ifdef __cplusplus
 }

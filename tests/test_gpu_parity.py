@@ -435,16 +435,6 @@ def test_update_scene_rebuilds_only_when_the_geometry_changed(golden, B200Render
     r.close()
 
 
-def test_traversal_reciprocal_equals_the_ieee_divide(golden, B200Renderer):
-    """Moeller-Trumbore's 1/det (geometry.cu:45) is computed by MUFU.RCP + one Newton step inside 2^-126 <= |det| < 8.5e37
-    and by the IEEE divide outside: the short form must equal the divide for EVERY float of its range."""
-    fs, _ = golden("tiny")
-    r = B200Renderer(fs, 16, 16, 1)
-    checked, bad = r.selftest_reciprocal()
-    r.close()
-    assert checked > 4_200_000_000 and bad == 0, (checked, bad)
-
-
 def test_degenerate_image_shapes_and_empty_ranks(golden, B200Renderer):
     """1x1 and odd-sized images, fewer row tiles than ranks (ranks that own nothing), zero samples."""
     fs, _ = golden("cornell")
