@@ -243,6 +243,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-smem-nodes", action="store_true", help="A/B: never stage BVH nodes in shared memory")
     ap.add_argument("--tight-bvh", default="auto", choices=["auto", "on", "off"], help="A/B: per-triangle tight BVH (DESIGN.md 2.4)")
+    ap.add_argument("--pad", default="auto", choices=["auto", "static", "dynamic"], help="A/B: where the tight BVH's boxes are inflated (DESIGN.md 2.4)")
     ap.add_argument("--stats", action="store_true", help="count node visits / triangle tests (slower; not a bench value)")
     ap.add_argument("--spp-per-wave", type=int, default=0, help="samples per pixel per wavefront batch (0 = auto, ~4M paths)")
     args = ap.parse_args()
@@ -277,7 +278,8 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     r = B200Renderer(fs, W, H, total_spp, device=local, rank=rank, world=world, profile=True, stream=stream,
                      spp_per_wave=args.spp_per_wave, smem_nodes=False if args.no_smem_nodes else None,
-                     tight_bvh={"auto": None, "on": True, "off": False}[args.tight_bvh], stats=args.stats)
+                     tight_bvh={"auto": None, "on": True, "off": False}[args.tight_bvh], stats=args.stats,
+                     dynamic_pad={"auto": None, "static": False, "dynamic": True}[args.pad])
 
     def barrier():
         if world > 1:
@@ -321,6 +323,7 @@ def main():
     launches = c1["kernel_launches"] - c0["kernel_launches"]
     stage = {k: round(c1["stage_ms"][k] - c0["stage_ms"][k], 3) for k in c1["stage_ms"]}
     tight_nodes, tight_always = r.tight_info()
+    pad_mode = ("off", "static", "dynamic")[r.tight_pad_mode()]
     per_ray = None
     if args.stats and rays > 0 and world == 1:
         per_ray = {"wide_nodes_per_ray": round((c1["node_visits"] - c0["node_visits"]) / rays, 2),
@@ -331,7 +334,8 @@ def main():
     # ---- e2e through the public API with HOST buffers: every step uploads the scene (host -> device), renders
     # spp_step samples per pixel and reads the RGBA8 frame back (device -> host), like one frame of an animation ----
     rr = B200Renderer(fs, W, H, spp_step, device=local, rank=rank, world=world, stream=stream, spp_per_wave=args.spp_per_wave,
-                      tight_bvh={"auto": None, "on": True, "off": False}[args.tight_bvh])
+                      tight_bvh={"auto": None, "on": True, "off": False}[args.tight_bvh],
+                      dynamic_pad={"auto": None, "static": False, "dynamic": True}[args.pad])
 
     # the frame lands in page-locked host memory (cudaMemcpyAsync at full PCIe rate, no staging copy)
     rr.h_imgPtr = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()
@@ -390,7 +394,7 @@ def main():
                             "host frame"},
             "gpu_launches": int(launches),
             "stage_ms": stage,
-            "tight_bvh": {"wide_nodes": tight_nodes, "split_triangles": tight_always, "per_ray": per_ray},
+            "tight_bvh": {"wide_nodes": tight_nodes, "split_triangles": tight_always, "pad": pad_mode, "per_ray": per_ray},
             "lane_stats": lane_stats,
             "roofline": {"bound": "hbm", "kernel": "k_traverse (BVH traversal of the extend and shadow rays)", "achieved": round(achieved, 2) if achieved else None,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,

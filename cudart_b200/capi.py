@@ -17,6 +17,8 @@ CRT_FLAG_NO_SMEM_NODES = 16
 CRT_FLAG_SMEM_TOP_LEVELS = 32
 CRT_FLAG_TIGHT_BVH = 64
 CRT_FLAG_NO_TIGHT_BVH = 128
+CRT_FLAG_DYNAMIC_PAD = 256
+CRT_FLAG_STATIC_PAD = 512
 CRT_MISS = 0xFFFFFFFF
 STAGES = ("raygen", "extend", "shade", "shadow", "accumulate")
 
@@ -77,8 +79,9 @@ SYMBOLS = {
     "crt_build_lights": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                    C.POINTER(C.c_uint32), C.POINTER(C.c_float)]),
     "crt_wide_bvh": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
-    "crt_tight_bvh": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
-                                C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p]),
+    "crt_tight_bvh": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p]),
+    "crt_tight_pad_mode": (C.c_int, [C.c_void_p]),
     "crt_tight_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "crt_lane_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64 * 8)]),
     "crt_scene_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

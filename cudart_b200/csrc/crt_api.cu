@@ -102,6 +102,7 @@ struct HostSceneCache {
     std::vector<float4> light_boxes;
     WideStats wide_stats{};
     uint32_t n_tight_wide = 0, tight_split = 0, n_front = 0;
+    bool dynamic_pad = false;
     F3 region_lo{FLT_MAX, FLT_MAX, FLT_MAX}, region_hi{-FLT_MAX, -FLT_MAX, -FLT_MAX};
     bool coords_bounded = false;
     std::vector<const void*> pinned;        // cudaHostRegister'ed staging arrays (async copies at full PCIe rate)
@@ -207,7 +208,8 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     Fingerprint fp;
     {
         const uint32_t hdr[6] = {s->n_tris, s->n_nodes, s->n_lights,
-                                 c->flags & (CRT_FLAG_REFERENCE_TOPOLOGY | CRT_FLAG_NO_TIGHT_BVH | CRT_FLAG_EXACT_VISIT | CRT_FLAG_TIGHT_BVH),
+                                 c->flags & (CRT_FLAG_REFERENCE_TOPOLOGY | CRT_FLAG_NO_TIGHT_BVH | CRT_FLAG_EXACT_VISIT | CRT_FLAG_TIGHT_BVH |
+                                            CRT_FLAG_DYNAMIC_PAD | CRT_FLAG_STATIC_PAD),
                                  (uint32_t)sizeof(RefTriangle), (uint32_t)sizeof(RefNode)};
         fingerprint_mix(fp, hdr, sizeof hdr);
         const float eye[4] = {cam_in->eye.x, cam_in->eye.y, cam_in->eye.z, cam_in->apertureWidth};
@@ -263,7 +265,8 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
         if (finite) {
             region_lo = {(float)(region_lo.x - m), (float)(region_lo.y - m), (float)(region_lo.z - m)};
             region_hi = {(float)(region_hi.x + m), (float)(region_hi.y + m), (float)(region_hi.z + m)};
-            build_tight_bvh(tris, s->n_tris, nodes, s->n_nodes, region_lo, region_hi, tight);
+            const PadMode pad_mode = (c->flags & CRT_FLAG_DYNAMIC_PAD) ? kPadDynamic : (c->flags & CRT_FLAG_STATIC_PAD) ? kPadStatic : kPadAuto;
+            build_tight_bvh(tris, s->n_tris, nodes, s->n_nodes, region_lo, region_hi, pad_mode, tight);
             ref_job.join();
             // Per reference leaf the builder already chose between individually inflated triangles and the leaf behind its
             // own box, and it may merge several reference leaves into one tight leaf (the gate keeps that exact), which the
@@ -296,6 +299,7 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     rec_job.join();
     hc.n_front = (uint32_t)(n_tight_wide ? n_tight_wide : wide.size());    // the tree the render path's rays walk
     hc.n_tight_wide = n_tight_wide;
+    hc.dynamic_pad = n_tight_wide && tight.dynamic_pad;
     hc.tight_records.swap(tight.records);
     if (!n_tight_wide) hc.tight_records.clear();
     hc.region_lo = region_lo; hc.region_hi = region_hi;
@@ -377,6 +381,7 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     if (!(c->flags & CRT_FLAG_NO_SMEM_NODES) && (n_front <= kMaxSmemNodes || (c->flags & CRT_FLAG_SMEM_TOP_LEVELS)))
         sc.n_smem_nodes = std::min<uint32_t>((uint32_t)n_front, kMaxSmemNodes);
     sc.tri_tight = n_tight_wide ? c->tri_tight.p : nullptr;
+    sc.dyn_pad = hc.dynamic_pad ? 1 : 0;
     sc.ref_root = n_tight_wide;
     sc.region_lo[0] = hc.region_lo.x; sc.region_lo[1] = hc.region_lo.y; sc.region_lo[2] = hc.region_lo.z;
     sc.region_hi[0] = hc.region_hi.x; sc.region_hi[1] = hc.region_hi.y; sc.region_hi[2] = hc.region_hi.z;
@@ -720,13 +725,18 @@ int crt_wide_bvh(const void* nodes, uint32_t n_nodes, void* wide_out, uint32_t c
 }
 
 
-int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t n_nodes, const float* region, float* tri_boxes_out,
+int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t n_nodes, const float* region, uint32_t pad_mode,
+                  float* tri_boxes_out, float* tri_pad_out, uint32_t* dynamic_out,
                   uint32_t* n_split_out, uint32_t* n_tight_nodes_out, uint32_t* n_wide_out, double* sah_out) {
-    if (!tris || !nodes || !region) return fail(CRT_ERR_INVALID, "crt_tight_bvh: null argument");
+    if (!tris || !nodes || !region || pad_mode > 2) return fail(CRT_ERR_INVALID, "crt_tight_bvh: bad argument");
     TightBvh tb;
     build_tight_bvh((const RefTriangle*)tris, n_tris, (const RefNode*)nodes, n_nodes, F3{region[0], region[1], region[2]},
-                    F3{region[3], region[4], region[5]}, tb);
+                    F3{region[3], region[4], region[5]}, (PadMode)pad_mode, tb);
     if (tri_boxes_out && tb.boxes.size() == 6 * (size_t)n_tris) memcpy(tri_boxes_out, tb.boxes.data(), tb.boxes.size() * sizeof(float));
+    if (dynamic_out) *dynamic_out = tb.dynamic_pad ? 1u : 0u;
+    if (tri_pad_out)         // (a1, b2) per triangle from its own packed cull bound; a node's terms are never smaller
+        for (uint32_t i = 0; i < n_tris; i++)
+            dynamic_pad_terms(pack_cull_bound(triangle_cull_bound(((const RefTriangle*)tris)[i])), tri_pad_out[2 * i], tri_pad_out[2 * i + 1]);
     if (n_split_out) *n_split_out = tb.n_split;
     if (n_tight_nodes_out) *n_tight_nodes_out = (uint32_t)tb.nodes.size();
     if (sah_out) {      // (nodes, triangles) expected per random line: tight tree, then the re-clustered reference-leaf tree
@@ -761,6 +771,8 @@ int crt_scene_info(const crt_ctx* c, uint64_t* host_rebuilds_out, uint64_t* uplo
     if (last_upload_bytes_out) *last_upload_bytes_out = c->scene_upload_bytes;
     return CRT_OK;
 }
+
+int crt_tight_pad_mode(const crt_ctx* c) { return c && c->tight_nodes ? (c->sc.dyn_pad ? 2 : 1) : 0; }
 
 int crt_tight_info(const crt_ctx* c, uint32_t* n_tight_wide_out, uint32_t* n_split_out) {
     if (!c) return fail(CRT_ERR_INVALID, "crt_tight_info: null ctx");

@@ -6,6 +6,7 @@
 //  * flatten_wide(): that binary tree re-flattened into the 128-byte 4-ary node the kernels read.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 namespace crt {
@@ -116,9 +117,31 @@ struct TightBvh {
                                             // triangle is tested (its own inflated box, or its reference leaf's exact box)
     uint32_t n_unbounded = 0;               // triangles too large for a distance bound (kept behind their reference leaf's box)
     uint32_t n_split = 0;                   // triangles that got their own inflated box
+    bool dynamic_pad = false;               // boxes are NOT inflated: the traversal pads them per visit (see below)
 };
+// Where the inflation of a triangle's box happens.  The bound on how far outside a triangle the fp32 test still accepts is
+// pad = 2 s (|T| + L) with |T| the distance from the ray origin to the triangle.
+//   kPadStatic : |T| <= D, the farthest point of the origin region - a fixed pad baked into the boxes.  Free at run time,
+//                but on a large fine mesh D / (triangle size) is huge: 0.16 units of pad on the 0.085-unit grid of the
+//                999 700-triangle terrain, i.e. every box is several triangles wide.
+//   kPadDynamic: the boxes stay tight and the traversal kernel grows a child box by  (1 - A) |T|max + 2 B  when it visits
+//                it, with (A, B) the node's cull bound (1 - A >= 2 s, B >= s L for every triangle below) and |T|max the
+//                L1 distance from the ray origin to the farthest corner of the child box: the pad follows the actual
+//                distance (about 1e-3 of it on the terrain) at ~13 more instructions per child.
+//   kPadAuto   : dynamic when the static inflation more than doubles the summed box area of the triangles.
+enum PadMode { kPadAuto = 0, kPadStatic = 1, kPadDynamic = 2 };
+// The two per-node constants of the dynamic pad as the kernel derives them from a packed cull bound (same float
+// expressions on both sides): pad = a1 * |T|max + b2.
+inline void dynamic_pad_terms(uint32_t packed_cull_bound, float& a1, float& b2) {
+    uint32_t a = packed_cull_bound & 0xffff0000u, b = packed_cull_bound << 16;
+    float A, B;
+    std::memcpy(&A, &a, 4);
+    std::memcpy(&B, &b, 4);
+    a1 = 1.001f * (1.00002f - A);           // 2 s (1 + 1e-3) and 2e-5 |T|max for the rounding of the slab test itself
+    b2 = 2.002f * B;
+}
 void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* ref_nodes, uint32_t n_ref_nodes,
-                     const F3& region_lo, const F3& region_hi, TightBvh& out);
+                     const F3& region_lo, const F3& region_hi, PadMode pad_mode, TightBvh& out);
 
 // Surface-area-heuristic cost of a binary tree in the reference's pre-order layout: expected (interior nodes visited,
 // triangles tested) by a random line that crosses the clip box (node boxes are clipped to it, so that two trees over

@@ -26,6 +26,7 @@ struct DScene {
     // Tight BVH (host_scene.h): its wide nodes are [0, ref_root), the reference-leaf tree starts at ref_root.  Rays that
     // qualify (culling allowed, origin inside the region the inflation was computed for) start at node 0.
     uint32_t ref_root;
+    int dyn_pad;               // tight-tree boxes are not inflated: pad each child box per visit (host_scene.h kPadDynamic)
     float region_lo[3], region_hi[3];
     RefCamera cam;
 };

@@ -36,7 +36,7 @@ class B200Renderer:
     def __init__(self, scene: FlatScene, width: int, height: int, samples: int = 10, *, device: int = -1, rank: int = 0,
                  world: int = 1, tile_rows: int = 8, seed: int = 1234, spp_per_wave: int = 0, exact_visit: bool = False,
                  profile: bool = False, stats: bool = False, reference_topology: bool = False, smem_nodes: bool | None = None,
-                 tight_bvh: bool | None = None, stream: int | None = None):
+                 tight_bvh: bool | None = None, dynamic_pad: bool | None = None, stream: int | None = None):
         self._lib = capi.lib()
         self.width, self.height, self.samples = int(width), int(height), int(samples)
         self.rank, self.world = rank, world
@@ -44,7 +44,8 @@ class B200Renderer:
         flags = (capi.CRT_FLAG_EXACT_VISIT if exact_visit else 0) | (capi.CRT_FLAG_PROFILE if profile else 0) \
             | (capi.CRT_FLAG_STATS if stats else 0) | (capi.CRT_FLAG_REFERENCE_TOPOLOGY if reference_topology else 0) \
             | (0 if smem_nodes is None else (capi.CRT_FLAG_SMEM_TOP_LEVELS if smem_nodes else capi.CRT_FLAG_NO_SMEM_NODES)) \
-            | (0 if tight_bvh is None else (capi.CRT_FLAG_TIGHT_BVH if tight_bvh else capi.CRT_FLAG_NO_TIGHT_BVH))
+            | (0 if tight_bvh is None else (capi.CRT_FLAG_TIGHT_BVH if tight_bvh else capi.CRT_FLAG_NO_TIGHT_BVH)) \
+            | (0 if dynamic_pad is None else (capi.CRT_FLAG_DYNAMIC_PAD if dynamic_pad else capi.CRT_FLAG_STATIC_PAD))
         opt = capi.Options(C.sizeof(capi.Options), device, rank, world, tile_rows, seed, spp_per_wave, flags, stream)
         h = C.c_void_p()
         capi.check(self._lib.crt_create(C.byref(desc), self.width, self.height, C.byref(opt), C.byref(h)))
@@ -140,6 +141,10 @@ class B200Renderer:
         a, b, n = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         capi.check(self._lib.crt_scene_info(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return int(a.value), int(b.value), int(n.value)
+
+    def tight_pad_mode(self) -> int:
+        """0 = the render path does not walk the tight BVH, 1 = pad baked into its boxes, 2 = padded per node visit."""
+        return int(self._lib.crt_tight_pad_mode(self._h))
 
     def accum_device_ptr(self):
         p, n = C.c_void_p(), C.c_size_t()

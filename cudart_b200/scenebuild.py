@@ -45,19 +45,28 @@ def wide_bvh(nodes: np.ndarray) -> np.ndarray:
     return out
 
 
-def tight_bvh(tris: np.ndarray, nodes: np.ndarray, region_lo, region_hi, sah: bool = False):
+PAD_AUTO, PAD_STATIC, PAD_DYNAMIC = 0, 1, 2
+
+
+def tight_bvh(tris: np.ndarray, nodes: np.ndarray, region_lo, region_hi, sah: bool = False, pad_mode: int = PAD_STATIC,
+              pads: bool = False):
     """The box a ray (starting inside the region) must pass before each triangle is tested in the tight BVH (f32[n, 6],
-    reference triangle order), plus (individually boxed triangles, binary nodes, wide nodes).  Introspection for tests."""
+    reference triangle order), plus (individually boxed triangles, binary nodes, wide nodes).  Introspection for tests.
+    pads=True appends (f32[n, 2] run-time pad terms (a1, b2) per triangle, whether the dynamic-pad tree was built)."""
     tris = np.ascontiguousarray(tris, TRIANGLE_DTYPE)
     nodes = np.ascontiguousarray(nodes, NODE_DTYPE)
     region = np.asarray(list(region_lo) + list(region_hi), np.float32)
     boxes = np.zeros((tris.shape[0], 6), np.float32)
     nb, nn, nw = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
     cost = np.zeros(4, np.float64)      # SAH (nodes, triangles) per random line: tight tree, reference-leaf tree
+    pad = np.zeros((tris.shape[0], 2), np.float32)
+    dyn = C.c_uint32(0)
     capi.check(capi.lib().crt_tight_bvh(tris.ctypes.data, tris.shape[0], nodes.ctypes.data, nodes.shape[0], region.ctypes.data,
-                                        boxes.ctypes.data, C.byref(nb), C.byref(nn), C.byref(nw), cost.ctypes.data))
+                                        int(pad_mode), boxes.ctypes.data, pad.ctypes.data, C.byref(dyn),
+                                        C.byref(nb), C.byref(nn), C.byref(nw), cost.ctypes.data))
     info = (int(nb.value), int(nn.value), int(nw.value))
-    return (boxes, info, cost) if sah else (boxes, info)
+    out = (boxes, info, cost) if sah else (boxes, info)
+    return out + (pad, bool(dyn.value)) if pads else out
 
 
 def assemble(tris, positions, mat_floats, mat_indices, camera, tex_dims=None, tex_offsets=None, tex_data=None,

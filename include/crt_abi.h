@@ -75,6 +75,8 @@ typedef struct crt_options {
 #define CRT_FLAG_SMEM_TOP_LEVELS 32u /* stage the top levels even when the tree does not fit entirely (A/B measurements) */
 #define CRT_FLAG_TIGHT_BVH 64u   /* force the tight per-triangle BVH (default: used when few triangles are too large for it) */
 #define CRT_FLAG_NO_TIGHT_BVH 128u /* never use the tight BVH: traverse the reference's leaves only            */
+#define CRT_FLAG_DYNAMIC_PAD 256u /* tight BVH with un-inflated boxes, padded per node visit in proportion to the distance */
+#define CRT_FLAG_STATIC_PAD 512u  /* tight BVH with the pad baked into its boxes (default: chosen per scene) */
 #define CRT_FLAG_STATS 4u        /* count wide-node fetches and triangle tests (slows traversal a little)  */
 
 typedef struct crt_ray { float ox, oy, oz, dx, dy, dz, tmin, tmax; } crt_ray;   /* == reference Ray       */
@@ -155,12 +157,18 @@ int crt_build_lights(void* tris, uint32_t n_tris, float* mat_floats, const int32
 /* Introspection of the wide (4-ary) flattening, for tests: writes up to cap 128-byte nodes. */
 int crt_wide_bvh(const void* nodes, uint32_t n_nodes, void* wide_out, uint32_t cap, uint32_t* n_wide_out);
 /* Introspection of the tight per-triangle BVH (no reference counterpart), for tests: region = lo.xyz, hi.xyz of
- * the box that holds every ray origin; tri_boxes_out (6 floats per triangle, reference order) receives the box a ray must
- * pass before the triangle is tested (the triangle's own inflated box, or its reference leaf's exact box when the leaf was
- * kept whole); *n_split_out = triangles with their own box; binary / wide node counts; sah_out = surface-area-heuristic
- * (nodes, triangles) per random line for the tight tree and for the re-clustered reference-leaf tree. */
-int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t n_nodes, const float* region, float* tri_boxes_out,
+ * the box that holds every ray origin; pad_mode 0 = chosen per scene, 1 = pad baked into the boxes, 2 = tight boxes padded
+ * by the traversal (*dynamic_out says which one was built); tri_boxes_out (6 floats per triangle, reference order) receives
+ * the box a ray must pass before the triangle is tested (the triangle's own box, or its reference leaf's exact box when the
+ * leaf was kept whole); tri_pad_out (2 floats per triangle) the terms (a1, b2) of the run-time pad a1 * |T|max + b2 the
+ * kernel would apply to a node holding only this triangle; *n_split_out = triangles with their own box; binary / wide
+ * node counts; sah_out = surface-area-heuristic (nodes, triangles) per random line for the tight tree and for the
+ * re-clustered reference-leaf tree. */
+int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t n_nodes, const float* region, uint32_t pad_mode,
+                  float* tri_boxes_out, float* tri_pad_out, uint32_t* dynamic_out,
                   uint32_t* n_split_out, uint32_t* n_tight_nodes_out, uint32_t* n_wide_out, double* sah_out /* 4 doubles or null */);
+/* 0 = this context's render path does not walk the tight BVH, 1 = static pad, 2 = dynamic pad. */
+int crt_tight_pad_mode(const crt_ctx* ctx);
 /* Whether this context's render path walks the tight BVH: its wide-node count (0 = off) and individually boxed triangles. */
 int crt_tight_info(const crt_ctx* ctx, uint32_t* n_tight_wide_out, uint32_t* n_split_out);
 /* With CRT_FLAG_STATS: where the traversal's SIMT lanes go.  out[0..2] = warp-level iterations of the interior-node loop,

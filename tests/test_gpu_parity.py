@@ -76,17 +76,20 @@ def test_closest_hit_is_independent_of_node_staging(golden, B200Renderer, smem):
         r.close()
 
 
-@pytest.mark.parametrize("tight", [True, False], ids=["tight-bvh", "reference-leaves"])
+@pytest.mark.parametrize("tight", ["static-pad", "dynamic-pad", None], ids=["tight-bvh-static-pad", "tight-bvh-dynamic-pad", "reference-leaves"])
 @pytest.mark.parametrize("name", SCENES)
 def test_closest_hit_is_independent_of_the_tight_bvh(golden, B200Renderer, name, tight):
-    """The per-triangle tight BVH (forced on, even for the Cornell boxes whose walls are all 'always tested') and the
-    reference-leaf tree give the reference's records bit for bit: golden rays, path rays, and grazing rays whose
-    determinant sits at the 1e-5 acceptance threshold (checked against exact-visit on the same device and the oracle)."""
+    """The per-triangle tight BVH (forced on, even for the Cornell boxes whose walls are all 'always tested'; with the pad
+    baked into its boxes and with tight boxes padded per node visit) and the reference-leaf tree give the reference's
+    records bit for bit: golden rays, path rays, and grazing rays whose determinant sits at the 1e-5 acceptance threshold
+    (checked against exact-visit on the same device and the oracle)."""
     from grazing import grazing_rays
     from cudart_b200.scenefile import RAY_DTYPE
     fs, g = golden(name)
-    r = B200Renderer(fs, g["W"], g["H"], tight_bvh=tight)
-    assert (r.tight_info()[0] > 0) == tight
+    kw = dict(tight_bvh=tight is not None, dynamic_pad=None if tight is None else tight == "dynamic-pad")
+    r = B200Renderer(fs, g["W"], g["H"], **kw)
+    assert (r.tight_info()[0] > 0) == (tight is not None)
+    assert r.tight_pad_mode() == {None: 0, "static-pad": 1, "dynamic-pad": 2}[tight]
     assert_hits_equal(r.trace_closest(g["rays"]), g["hits"])
     o, d, _ = grazing_rays(fs, 300_000, seed=17)
     rays = np.zeros(len(o), RAY_DTYPE)
@@ -98,7 +101,7 @@ def test_closest_hit_is_independent_of_the_tight_bvh(golden, B200Renderer, name,
     big = fs.with_resolution(160, 120)
     osc = orc.OracleScene(big)
     _, prays = osc.render_accum(4, rng=orc.RNG_COUNTER, seed=5, threads=1, ray_log_cap=1 << 21)
-    r = B200Renderer(big, 160, 120, tight_bvh=tight)
+    r = B200Renderer(big, 160, 120, **kw)
     assert_hits_equal(r.trace_closest(prays), osc.trace_closest(prays))
     r.close()
 
@@ -108,12 +111,13 @@ def test_render_is_bitwise_independent_of_the_tight_bvh(golden, B200Renderer, na
     """Whole pipeline (extend + targeted shadow rays): identical closest hits give identical radiance sums, bit for bit."""
     fs, g = golden(name)
     sums = []
-    for tight in (True, False):
-        r = B200Renderer(fs, g["W"], g["H"], seed=3, tight_bvh=tight)
+    for tight, dyn in ((True, False), (True, True), (False, None)):
+        r = B200Renderer(fs, g["W"], g["H"], seed=3, tight_bvh=tight, dynamic_pad=dyn)
         r.render(8)
         sums.append(r.accum().copy())
         r.close()
-    assert np.array_equal(sums[0].view(np.uint32), sums[1].view(np.uint32))
+    assert np.array_equal(sums[0].view(np.uint32), sums[2].view(np.uint32))
+    assert np.array_equal(sums[1].view(np.uint32), sums[2].view(np.uint32))
 
 
 def test_empty_and_ragged_ray_batches(golden, B200Renderer):

@@ -12,13 +12,33 @@ from grazing import f32, grazing_rays, moeller_trumbore, region_of
 from oracle import orc
 
 
-def box_pass(boxes, o, d):
-    """The traversal kernel's min/max slab test (kernels.cu trace_queue, `fast` path) in numpy float32."""
+def box_pass(boxes, o, d, pad=None):
+    """The traversal kernel's min/max slab test (kernels.cu trace_queue, `fast` path) in numpy float32.  pad = (a1, b2)
+    per box: the dynamic-pad form, every side grown by a1 * |T|max + b2 with |T|max the L1 distance from the origin to the
+    farthest corner of the box."""
     with np.errstate(all="ignore"):
         inv = (f32(1) / d).astype(f32)
-        a0 = ((boxes[:, :3] - o).astype(f32) * inv).astype(f32)
-        a1 = ((boxes[:, 3:] - o).astype(f32) * inv).astype(f32)
-        return np.minimum(a0, a1).max(1) <= np.maximum(a0, a1).min(1), np.all(np.abs(inv) < 1e28, 1)
+        s0, s1 = (boxes[:, :3] - o).astype(f32), (boxes[:, 3:] - o).astype(f32)
+        a0, a1 = (s0 * inv).astype(f32), (s1 * inv).astype(f32)
+        near, far = np.minimum(a0, a1), np.maximum(a0, a1)
+        if pad is not None:
+            m = np.maximum(np.abs(s0), np.abs(s1))
+            tm = ((m[:, 0] + m[:, 1]).astype(f32) + m[:, 2]).astype(f32)
+            P = (pad[:, 0].astype(np.float64) * tm + pad[:, 1]).astype(f32)                 # fmaf
+            p = (P[:, None] * np.abs(inv)).astype(f32)
+            near, far = (near - p).astype(f32), (far + p).astype(f32)
+        return near.max(1) <= far.min(1), np.all(np.abs(inv) < 1e28, 1)
+
+
+MODES = {"static-pad": 1, "dynamic-pad": 2}
+
+
+def boxes_and_pads(fs, lo, hi, mode):
+    """(boxes, pad terms or None, info) of the tight tree built in the given pad mode."""
+    from cudart_b200.scenebuild import tight_bvh
+    boxes, info, pad, dyn = tight_bvh(fs.tris, fs.nodes, lo, hi, pad_mode=MODES[mode], pads=True)
+    assert dyn == (mode == "dynamic-pad")
+    return boxes, (pad if dyn else None), info
 
 
 def leaf_boxes(fs):
@@ -32,17 +52,17 @@ def leaf_boxes(fs):
     return in_leaf, box
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", SCENES)
-def test_accepted_grazing_hits_pass_the_inflated_box(golden, name):
-    from cudart_b200.scenebuild import tight_bvh
+def test_accepted_grazing_hits_pass_the_inflated_box(golden, name, mode):
     fs, _ = golden(name)
     lo, hi = region_of(fs)
-    boxes, (n_big, n_nodes, n_wide) = tight_bvh(fs.tris, fs.nodes, lo, hi)
+    boxes, pad, (n_big, n_nodes, n_wide) = boxes_and_pads(fs, lo, hi, mode)
     assert n_nodes > 0 and n_wide > 0
     o, d, k = grazing_rays(fs, 200_000)
     t = fs.tris
     acc, _, _, _, det = moeller_trumbore(o, d, t["v1"][k], t["e1"][k], t["e2"][k])
-    passed, fast = box_pass(boxes[k], o, d)
+    passed, fast = box_pass(boxes[k], o, d, None if pad is None else pad[k])
     acc &= fast
     assert acc.sum() > 20_000 and (acc & (np.abs(det) < 3e-5)).sum() > 2_000      # the generator reaches the threshold regime
     # a triangle with its own inflated box: every accepted hit passes it.  A triangle kept behind its reference leaf's box
@@ -54,29 +74,29 @@ def test_accepted_grazing_hits_pass_the_inflated_box(golden, name):
     assert not (acc & gate & ~passed).any()
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", SCENES)
-def test_path_ray_winners_pass_their_inflated_box(golden, name):
-    from cudart_b200.scenebuild import tight_bvh
+def test_path_ray_winners_pass_their_inflated_box(golden, name, mode):
     fs, _ = golden(name)
     small = fs.with_resolution(64, 48)
     lo, hi = region_of(small)
-    boxes, _ = tight_bvh(small.tris, small.nodes, lo, hi)
+    boxes, pad, _ = boxes_and_pads(small, lo, hi, mode)
     osc = orc.OracleScene(small)
     _, rays = osc.render_accum(4, rng=orc.RNG_COUNTER, seed=11, threads=1, ray_log_cap=64 * 48 * 4 * 12)
     want = osc.trace_closest(rays)
     hit = want["tri"] != 0xFFFFFFFF
     o, d = rays["o"][hit], rays["d"][hit]
     assert np.all((o >= lo) & (o <= hi)), "path ray origins must stay inside the region the bound is valid for"
-    passed, fast = box_pass(boxes[want["tri"][hit]], o, d)
+    passed, fast = box_pass(boxes[want["tri"][hit]], o, d, None if pad is None else pad[want["tri"][hit]])
     assert not (fast & ~passed).any()
 
 
-def test_boxes_contain_their_triangle_and_unsplit_leaves_keep_the_reference_box(golden):
-    from cudart_b200.scenebuild import tight_bvh
+@pytest.mark.parametrize("mode", MODES)
+def test_boxes_contain_their_triangle_and_unsplit_leaves_keep_the_reference_box(golden, mode):
     for name in SCENES:
         fs, _ = golden(name)
         lo, hi = region_of(fs)
-        boxes, (n_split, n_nodes, _) = tight_bvh(fs.tris, fs.nodes, lo, hi)
+        boxes, _, (n_split, n_nodes, _) = boxes_and_pads(fs, lo, hi, mode)
         t = fs.tris
         v1 = t["v1"].astype(np.float64)
         in_leaf, leaf_box = leaf_boxes(fs)

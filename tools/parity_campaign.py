@@ -5,8 +5,8 @@ harvested secondary and shadow rays").  For every fixture scene:
   1. harvest every ray the path loop hands to the traversal (camera, bounce and shadow rays) from the CPU oracle,
      in parallel over row bands;
   2. trace them with the oracle's restatement of the reference traversal (pinned bit-exact to the reference);
-  3. trace them on the B200 through the C ABI: the render path's traversal with the tight per-triangle BVH forced on and
-     forced off (distance-culled both), and exact-visit (no culling, reference leaves only);
+  3. trace them on the B200 through the C ABI: the render path's traversal with the tight per-triangle BVH forced on (pad baked into
+     its boxes, and tight boxes padded per node visit) and forced off (distance-culled all three), and exact-visit (no culling, reference leaves only);
   4. compare (triangle index, t, u, v) bit for bit.
 
 usage (GPU box): python tools/parity_campaign.py [--rays 1e7] [--out profiles/r01_parity_campaign.json]
@@ -65,10 +65,11 @@ def main():
         t2 = time.time()
         rec = {"rays": int(len(rays)), "hits": int((want["tri"] != 0xFFFFFFFF).sum()), "harvest_s": round(t1 - t0, 1),
                "oracle_trace_s": round(t2 - t1, 1)}
-        for mode, exact, tight in (("culled_tight_bvh", False, True), ("culled", False, False), ("exact_visit", True, False)):
-            r = B200Renderer(fs, W, H, tight_bvh=tight)
-            if mode == "culled_tight_bvh":
-                rec["tight_bvh_wide_nodes"], rec["tight_bvh_split_triangles"] = r.tight_info()
+        for mode, exact, tight, dyn in (("culled_tight_bvh", False, True, False), ("culled_tight_bvh_dynamic_pad", False, True, True),
+                                        ("culled", False, False, None), ("exact_visit", True, False, None)):
+            r = B200Renderer(fs, W, H, tight_bvh=tight, dynamic_pad=dyn)
+            if tight:
+                rec[mode + "_wide_nodes"], rec[mode + "_split_triangles"] = r.tight_info()
             got = r.trace_closest(rays, exact_visit=exact)
             r.close()
             bad = (got["tri"] != want["tri"]) | (got["t"].view(np.uint32) != want["t"].view(np.uint32)) | \
@@ -81,7 +82,8 @@ def main():
         print(name, rec, flush=True)
     json.dump({"what": "closest-hit records of the B200 path vs the oracle restatement of the reference traversal, bit for bit",
                "image_for_harvest": [W, H], "results": results}, open(a.out, "w"), indent=1)
-    bad = sum(v["culled_tight_bvh_mismatches"] + v["culled_mismatches"] + v["exact_visit_mismatches"] for v in results.values())
+    bad = sum(v["culled_tight_bvh_mismatches"] + v["culled_tight_bvh_dynamic_pad_mismatches"] + v["culled_mismatches"] +
+              v["exact_visit_mismatches"] for v in results.values())
     sys.exit(1 if bad else 0)
 
 
