@@ -734,9 +734,11 @@ int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t
                     F3{region[3], region[4], region[5]}, (PadMode)pad_mode, tb);
     if (tri_boxes_out && tb.boxes.size() == 6 * (size_t)n_tris) memcpy(tri_boxes_out, tb.boxes.data(), tb.boxes.size() * sizeof(float));
     if (dynamic_out) *dynamic_out = tb.dynamic_pad ? 1u : 0u;
-    if (tri_pad_out)         // (a1, b2) per triangle from its own packed cull bound; a node's terms are never smaller
-        for (uint32_t i = 0; i < n_tris; i++)
-            dynamic_pad_terms(pack_cull_bound(triangle_cull_bound(((const RefTriangle*)tris)[i])), tri_pad_out[2 * i], tri_pad_out[2 * i + 1]);
+    if (tri_pad_out)         // (a1, b2) per triangle from its own cull bound; a node's terms are never smaller
+        for (uint32_t i = 0; i < n_tris; i++) {
+            const CullBound b = triangle_cull_bound(((const RefTriangle*)tris)[i]);
+            dynamic_pad_terms(b.A, b.B, tri_pad_out[2 * i], tri_pad_out[2 * i + 1]);
+        }
     if (n_split_out) *n_split_out = tb.n_split;
     if (n_tight_nodes_out) *n_tight_nodes_out = (uint32_t)tb.nodes.size();
     if (sah_out) {      // (nodes, triangles) expected per random line: tight tree, then the re-clustered reference-leaf tree

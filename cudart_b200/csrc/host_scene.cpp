@@ -394,7 +394,9 @@ WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, const RefTriangle
     // A slot is either a binary node index or (for chunks of an oversized reference leaf) an explicit range.
     struct Slot { uint32_t bin; uint32_t first, count; bool chunk; };
 
+    std::vector<CullBound> child_cb;             // 4 per wide node, unpacked
     auto new_wide = [&]() {
+        child_cb.resize(child_cb.size() + 4, CullBound{1.f, 0.f});
         out.emplace_back();
         WideNode& w = out.back();
         std::memset(&w, 0, sizeof w);
@@ -454,6 +456,7 @@ WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, const RefTriangle
                 w.lox[c] = bn.mn.x; w.loy[c] = bn.mn.y; w.loz[c] = bn.mn.z;
                 w.hix[c] = bn.mx.x; w.hiy[c] = bn.mx.y; w.hiz[c] = bn.mx.z;
                 w.aux[c] = pack_cull_bound(cb[s.bin]);
+                child_cb[4 * (size_t)cur + c] = cb[s.bin];
                 if (s.chunk) {
                     w.child[c] = leaf_ref(s.first, s.count);
                     st.n_leaf_refs++;
@@ -473,28 +476,32 @@ WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, const RefTriangle
                 w.lox[3] = bn.mn.x; w.loy[3] = bn.mn.y; w.loz[3] = bn.mn.z;
                 w.hix[3] = bn.mx.x; w.hiy[3] = bn.mx.y; w.hiz[3] = bn.mx.z;
                 w.aux[3] = pack_cull_bound(cb[it.bin]);
+                child_cb[4 * (size_t)cur + 3] = cb[it.bin];
                 w.child[3] = (int32_t)cont;
                 cur = cont;
             }
         }
     }
-    // One cull bound per wide node (the loosest of its children), replicated in the four aux words: the kernel decodes
-    // it once per node instead of once per child.
-    for (WideNode& w : out) {
+    // One cull bound per wide node (the loosest of its children): the kernel decodes it once per node instead of once
+    // per child.  aux[0] (and [3]) carry it packed; aux[1], aux[2] the float terms of the dynamic pad.
+    for (size_t n = 0; n < out.size(); n++) {
+        WideNode& w = out[n];
         float A = 1.f, B = 0.f;
         bool any = false;
         for (int c = 0; c < 4; c++) {
             if (w.child[c] == kEmptyChild) continue;
-            uint32_t a = w.aux[c] & 0xffff0000u, b = w.aux[c] << 16;
-            float fa, fb;
-            std::memcpy(&fa, &a, 4);
-            std::memcpy(&fb, &b, 4);
-            A = any ? std::min(A, fa) : fa;
-            B = any ? std::max(B, fb) : fb;
+            const CullBound& b = child_cb[4 * n + c];
+            A = any ? std::min(A, b.A) : b.A;
+            B = any ? std::max(B, b.B) : b.B;
             any = true;
         }
-        const uint32_t packed = pack_cull_bound({any ? A : 0.f, any ? B : INFINITY});
-        for (int c = 0; c < 4; c++) w.aux[c] = packed;
+        if (!any) { A = 0.f; B = INFINITY; }
+        const uint32_t packed = pack_cull_bound({A, B});
+        float a1, b2;
+        dynamic_pad_terms(A, B, a1, b2);
+        w.aux[0] = w.aux[3] = packed;
+        std::memcpy(&w.aux[1], &a1, 4);
+        std::memcpy(&w.aux[2], &b2, 4);
     }
     st.n_wide = (uint32_t)out.size();
     return st;

@@ -44,8 +44,8 @@ static_assert(sizeof(RefCamera) == 72, "reference Camera layout");
 struct WideNode {
     float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
     int32_t child[4];         // >= 0: index of a WideNode; < 0: leaf, see leaf_ref(); kEmptyChild: unused slot
-    uint32_t aux[4];          // packed CullBound (pack_cull_bound) of the node = loosest of its children's subtrees,
-                              // replicated in all four words (the kernel decodes word 0)
+    uint32_t aux[4];          // [0], [3]: packed CullBound (pack_cull_bound) of the node = loosest of its children's
+                              // subtrees; [1], [2]: the float terms (a1, b2) of the dynamic pad (dynamic_pad_terms)
 };
 static_assert(sizeof(WideNode) == 128, "wide node is one 128-byte line");
 
@@ -126,18 +126,16 @@ struct TightBvh {
 //                999 700-triangle terrain, i.e. every box is several triangles wide.
 //   kPadDynamic: the boxes stay tight and the traversal kernel grows a child box by  (1 - A) |T|max + 2 B  when it visits
 //                it, with (A, B) the node's cull bound (1 - A >= 2 s, B >= s L for every triangle below) and |T|max the
-//                L1 distance from the ray origin to the farthest corner of the child box: the pad follows the actual
+//                distance from the ray origin to the farthest corner of the child box: the pad follows the actual
 //                distance (about 1e-3 of it on the terrain) at ~13 more instructions per child.
 //   kPadAuto   : dynamic when the static inflation more than doubles the summed box area of the triangles.
 enum PadMode { kPadAuto = 0, kPadStatic = 1, kPadDynamic = 2 };
-// The two per-node constants of the dynamic pad as the kernel derives them from a packed cull bound (same float
-// expressions on both sides): pad = a1 * |T|max + b2.
-inline void dynamic_pad_terms(uint32_t packed_cull_bound, float& a1, float& b2) {
-    uint32_t a = packed_cull_bound & 0xffff0000u, b = packed_cull_bound << 16;
-    float A, B;
-    std::memcpy(&A, &a, 4);
-    std::memcpy(&B, &b, 4);
-    a1 = 1.001f * (1.00002f - A);           // 2 s (1 + 1e-3) and 2e-5 |T|max for the rounding of the slab test itself
+// The two per-node constants of the dynamic pad, pad = a1 * |T|max + b2, from the (unpacked) cull bound of the node:
+// 1 - A = 2 s + 1e-6 and B = s L (1 + 1e-6), so a1 >= 2 s (1 + 1e-3) + 2e-5 (the second term covers the rounding of the
+// slab test itself, 3 eps |T|max per plane) and b2 >= 2 s L.  Stored as plain floats in aux[1], aux[2] of a WideNode:
+// the bf16 halves of the packed cull bound would round 1 - A = 1e-3 up to 2..4e-3.
+inline void dynamic_pad_terms(float A, float B, float& a1, float& b2) {
+    a1 = 1.001f * (1.00002f - A);
     b2 = 2.002f * B;
 }
 void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* ref_nodes, uint32_t n_ref_nodes,

@@ -14,17 +14,17 @@ from oracle import orc
 
 def box_pass(boxes, o, d, pad=None):
     """The traversal kernel's min/max slab test (kernels.cu trace_queue, `fast` path) in numpy float32.  pad = (a1, b2)
-    per box: the dynamic-pad form, every side grown by a1 * |T|max + b2 with |T|max the L1 distance from the origin to the
-    farthest corner of the box."""
+    per box: the dynamic-pad form, every side grown by a1 * |T|max + b2 with |T|max the distance from the origin to the
+    farthest corner of the box (the kernel multiplies a1 by 1.0001 to cover its approximate square root; not here)."""
     with np.errstate(all="ignore"):
         inv = (f32(1) / d).astype(f32)
         s0, s1 = (boxes[:, :3] - o).astype(f32), (boxes[:, 3:] - o).astype(f32)
         a0, a1 = (s0 * inv).astype(f32), (s1 * inv).astype(f32)
         near, far = np.minimum(a0, a1), np.maximum(a0, a1)
         if pad is not None:
-            m = np.maximum(np.abs(s0), np.abs(s1))
-            tm = ((m[:, 0] + m[:, 1]).astype(f32) + m[:, 2]).astype(f32)
-            P = (pad[:, 0].astype(np.float64) * tm + pad[:, 1]).astype(f32)                 # fmaf
+            m = np.maximum(np.abs(s0), np.abs(s1)).astype(np.float64)
+            tm = np.sqrt((m * m).sum(1)).astype(f32)                                        # fma chain + sqrt.approx (2 ulp)
+            P = (pad[:, 0].astype(np.float64) * tm + pad[:, 1]).astype(f32)                 # fmaf; the kernel's a1 is 1.0001 x this one
             p = (P[:, None] * np.abs(inv)).astype(f32)
             near, far = (near - p).astype(f32), (far + p).astype(f32)
         return near.max(1) <= far.min(1), np.all(np.abs(inv) < 1e28, 1)
