@@ -750,13 +750,15 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
             }
         });
         if (pad_mode == kPadAuto) {
-            // The baked-in pad is free at run time; the per-visit pad costs ~13 instructions per child.  It pays when the
-            // fixed pad is comparable to the triangles themselves (mean pad / longest edge: cornellSphere 0.01, monkeys 0.4,
-            // terrain 999 700: 1.3, where it takes 26 -> 5 triangle tests off a random line).
+            // The baked-in pad is free at run time; the per-visit pad costs ~16 instructions per child and takes the
+            // loosest (a1, b2) of a node's children, so one wall-sized triangle pads its whole node.  It pays when the
+            // fixed pad is comparable to the triangles themselves.  Mean pad / longest edge and the measured outcome
+            // (profiles/r01z_pad_ab.txt): cornellSphere 0.02 (1980 static vs 882 dynamic Msamples/s), cornell 0.23,
+            // monkeys 0.44 (803 vs 932), terrain 999 700: 0.75 (343 vs 447), terrain 131 074: 2.1 (232 vs 320).
             double sum = 0, cnt = 0;
             for (uint32_t i = 0; i < n_tris; i++)
                 if (infl_ok[i]) { sum += rel_pad[i]; cnt += 1; }
-            pad_mode = (cnt > 0 && sum / cnt > 0.5) ? kPadDynamic : kPadStatic;
+            pad_mode = (cnt > 0 && sum / cnt > 0.3) ? kPadDynamic : kPadStatic;
         }
         out.dynamic_pad = pad_mode == kPadDynamic;
         if (out.dynamic_pad) { infl_mn.swap(tight_mn); infl_mx.swap(tight_mx); }
