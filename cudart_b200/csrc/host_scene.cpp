@@ -720,11 +720,7 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
     out = TightBvh();
     if (n_tris == 0) return;
     out.boxes.assign(6 * (size_t)n_tris, 0.f);
-    // bounded primitives / groups of triangles without a distance bound / (dynamic pad only) bounded primitives whose
-    // error scale s is far above the scene's typical one: a node pads all its children with the loosest (a1, b2) below
-    // it, so one wall-sized triangle among small ones would pad the whole node (cornellSphere's walls: 1980 -> 882
-    // Msamples/s).  They get their own subtree, like the unbounded ones.
-    TightBuilder tb, ub, lb;
+    TightBuilder tb, ub;                    // bounded primitives / groups of triangles without a distance bound
     tb.prims.reserve(n_tris);
     tb.members.reserve(n_tris);
     std::vector<uint32_t> leaf_of(n_tris, 0xffffffffu);
@@ -759,6 +755,8 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
             // fixed pad is comparable to the triangles themselves.  Mean pad / longest edge and the measured outcome
             // (profiles/r01z_pad_ab.txt): cornellSphere 0.02 (1980 static vs 882 dynamic Msamples/s), cornell 0.23,
             // monkeys 0.44 (803 vs 932), terrain 999 700: 0.75 (343 vs 447), terrain 131 074: 2.1 (232 vs 320).
+            // (Moving the large-s primitives into a subtree of their own, like the unbounded ones, was measured too:
+            // every ray then walks two overlapping trees - monkeys 932 -> 712, cornellSphere 882 -> 915; not kept.)
             double sum = 0, cnt = 0;
             for (uint32_t i = 0; i < n_tris; i++)
                 if (infl_ok[i]) { sum += rel_pad[i]; cnt += 1; }
@@ -766,17 +764,6 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
         }
         out.dynamic_pad = pad_mode == kPadDynamic;
         if (out.dynamic_pad) { infl_mn.swap(tight_mn); infl_mx.swap(tight_mx); }
-    }
-    float s_large = INFINITY;               // primitives with s above this go to `lb`
-    auto s_of = [&](uint32_t i) { return 0.5f * (1.f - triangle_cull_bound(tris[i]).A); };      // A = 1 - 2 s - 1e-6
-    if (out.dynamic_pad) {
-        std::vector<float> ss;
-        ss.reserve(n_tris);
-        for (uint32_t i = 0; i < n_tris; i++) if (infl_ok[i]) ss.push_back(s_of(i));
-        if (!ss.empty()) {
-            std::nth_element(ss.begin(), ss.begin() + ss.size() / 2, ss.end());
-            s_large = 8.f * ss[ss.size() / 2];
-        }
     }
     std::vector<uint32_t> bounded, unbounded, one(1);
     std::vector<F3> bmn, bmx;
@@ -818,20 +805,18 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
         if (split_cost < 0.7 * group_cost) {
             for (size_t j = 0; j < bounded.size(); j++) {
                 one[0] = bounded[j];
-                add_prim(s_of(bounded[j]) > s_large ? lb : tb, one, bmn[j], bmx[j]);
+                add_prim(tb, one, bmn[j], bmx[j]);
                 set_box(bounded[j], bmn[j], bmx[j]);
             }
             out.n_split += (uint32_t)bounded.size();
         } else {
-            float s_max = 0.f;
-            for (uint32_t i : bounded) s_max = std::max(s_max, s_of(i));
-            add_prim(s_max > s_large ? lb : tb, bounded, gmn, gmx);
+            add_prim(tb, bounded, gmn, gmx);
             for (uint32_t i : bounded) set_box(i, gmn, gmx);
         }
     }
-    if (tb.prims.empty() && ub.prims.empty() && lb.prims.empty()) { out = TightBvh(); return; }
-    // One tree: the non-empty groups hang off a chain at the root - (no distance bound, (large s, everything else)).
-    // Keeping them apart keeps their loose cull bound and pad out of every other node's (flatten_wide takes the loosest).
+    if (tb.prims.empty() && ub.prims.empty()) { out = TightBvh(); return; }
+    // One tree: root = (subtree of the groups without a distance bound, subtree of everything else).  Keeping the former
+    // apart keeps their (A = 0, B = inf) cull bound out of every other node's bound (flatten_wide takes the loosest).
     std::vector<RefNode>& nodes = out.nodes;
     std::vector<uint32_t> order;
     auto append = [&](TightBuilder& bd) {          // build bd's tree and splice it behind `nodes` / `order`
@@ -844,22 +829,16 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
         order.insert(order.end(), bd.order.begin(), bd.order.end());
         return nbase;
     };
-    std::vector<TightBuilder*> parts;
-    for (TightBuilder* bd : {&ub, &lb, &tb}) if (!bd->prims.empty()) parts.push_back(bd);
-    std::vector<uint32_t> links;                             // interior nodes of the chain: (this group, the rest)
-    for (size_t k = 0; k < parts.size(); k++) {
-        if (k + 1 < parts.size()) { links.push_back((uint32_t)nodes.size()); nodes.emplace_back(); }
-        append(*parts[k]);
-        if (k + 1 < parts.size()) {
-            RefNode& ln = nodes[links.back()];
-            std::memset(&ln, 0, sizeof ln);
-            ln.offset = (int32_t)nodes.size();               // the rest starts right behind this group's subtree
-        }
-    }
-    for (size_t k = links.size(); k-- > 0;) {                // boxes bottom-up: the first child follows its parent
-        RefNode& ln = nodes[links[k]];
-        ln.mn = lo3(nodes[links[k] + 1].mn, nodes[(uint32_t)ln.offset].mn);
-        ln.mx = hi3(nodes[links[k] + 1].mx, nodes[(uint32_t)ln.offset].mx);
+    if (!tb.prims.empty() && !ub.prims.empty()) {
+        nodes.emplace_back();
+        append(ub);
+        const uint32_t second = append(tb);
+        RefNode& rt = nodes[0];
+        std::memset(&rt, 0, sizeof rt);
+        rt.mn = lo3(nodes[1].mn, nodes[second].mn); rt.mx = hi3(nodes[1].mx, nodes[second].mx);
+        rt.offset = (int32_t)second;
+    } else {
+        append(tb.prims.empty() ? ub : tb);
     }
     const uint32_t n_used = (uint32_t)order.size();          // triangles in no reference leaf are never reached: left out
     out.records.resize(n_used);
