@@ -39,6 +39,7 @@ WORKLOADS = {
     "cornell_256": ("cornell", 256, 256, 16),
     "terrain1m_1080p": ("terrain707", 1920, 1080, 256),      # BASELINE config 4: 999 700 procedural triangles
     "terrain131k_1080p": ("terrain256", 1920, 1080, 256),
+    "terrain8k_256": ("terrain64", 256, 256, 16),             # small dynamic-pad scene for compute-sanitizer runs
 }
 SPP_PER_STEP = 64
 L2_BYTES = 126 * 1024 * 1024
