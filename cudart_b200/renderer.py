@@ -152,12 +152,10 @@ class B200Renderer:
         return int(p.value), int(n.value)
 
     def resolve_gathered(self, d_gathered: int, want_rgba8: bool = True, want_f32: bool = False):
-        rgba = np.zeros((self.height, self.width, 4), np.uint8) if want_rgba8 else None
+        rgba = self.h_imgPtr if want_rgba8 else None          # in place: the caller may have made it page-locked
         f32 = np.empty((self.height, self.width, 3), np.float32) if want_f32 else None
         capi.check(self._lib.crt_resolve_gathered(self._h, d_gathered, rgba.ctypes.data if want_rgba8 else None,
                                                   f32.ctypes.data if want_f32 else None))
-        if want_rgba8:
-            self.h_imgPtr = rgba
         return rgba, f32
 
     def close(self) -> None:
