@@ -186,40 +186,11 @@ int check_kernel(const char* what) {
 
 }  // namespace
 
-// Validate, re-flatten and upload a scene into a context (crt_create and crt_update_scene).
-static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_t H) {
-    // ---- scene: re-flatten on the host, upload ----
+// Everything upload_scene derives from the caller's triangles and nodes on the host, into the context's HostSceneCache.
+static int derive_host_scene(crt_ctx* c, const crt_scene_desc* s, const Fingerprint& fp) {
     const RefTriangle* tris = (const RefTriangle*)s->tris;
     const RefNode* nodes = (const RefNode*)s->nodes;
-    for (uint32_t k = 0; k < s->n_nodes; k++) {
-        const RefNode& nd = nodes[k];
-        bool ok = nd.nTris > 0 ? ((uint32_t)nd.offset + (uint32_t)nd.nTris <= s->n_tris)
-                               : (nd.offset > (int32_t)k && (uint32_t)nd.offset < s->n_nodes && k + 1 < s->n_nodes);
-        if (!ok) return (fail(CRT_ERR_INVALID, "scene: BVH node %u is malformed", k));
-    }
-    if (s->n_lights == 0 || !s->light_indices || !(s->lights_area > 0.f))
-        return fail(CRT_ERR_INVALID, "scene: no emissive triangles (the reference divides by a zero light area and indexes an empty "
-                                     "light list in that case, SURVEY.md D13)");
-    for (uint32_t k = 0; k < s->n_lights; k++)
-        if (s->light_indices[k] >= s->n_tris) return (fail(CRT_ERR_INVALID, "scene: light index out of range"));
-    // Fingerprint of everything the derived arrays depend on: geometry, BVH, lights, the flags that pick the trees, and
-    // the camera position / aperture (the tight tree's region of valid ray origins contains the eye).
-    const RefCamera* cam_in = (const RefCamera*)s->camera;
-    Fingerprint fp;
-    {
-        const uint32_t hdr[6] = {s->n_tris, s->n_nodes, s->n_lights,
-                                 c->flags & (CRT_FLAG_REFERENCE_TOPOLOGY | CRT_FLAG_NO_TIGHT_BVH | CRT_FLAG_EXACT_VISIT | CRT_FLAG_TIGHT_BVH |
-                                            CRT_FLAG_DYNAMIC_PAD | CRT_FLAG_STATIC_PAD),
-                                 (uint32_t)sizeof(RefTriangle), (uint32_t)sizeof(RefNode)};
-        fingerprint_mix(fp, hdr, sizeof hdr);
-        const float eye[4] = {cam_in->eye.x, cam_in->eye.y, cam_in->eye.z, cam_in->apertureWidth};
-        fingerprint_mix(fp, eye, sizeof eye);
-        fingerprint_mix(fp, s->light_indices, sizeof(uint32_t) * (size_t)s->n_lights);
-        fingerprint_mix(fp, nodes, sizeof(RefNode) * (size_t)s->n_nodes);
-        fingerprint_mix(fp, tris, sizeof(RefTriangle) * (size_t)s->n_tris);
-    }
     HostSceneCache& hc = c->host_scene;
-    if (!(hc.valid && hc.fp == fp)) {
     hc.valid = false;
     hc.unpin();
     // The reference-leaf tree (re-cluster + 4-ary flatten), the shading records and the tight BVH below are independent
@@ -327,6 +298,45 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     hc.fp = fp;
     hc.valid = true;
     c->scene_rebuilds++;
+    return CRT_OK;
+}
+
+// Validate, re-flatten and upload a scene into a context (crt_create and crt_update_scene).
+static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_t H) {
+    // ---- scene: re-flatten on the host, upload ----
+    const RefTriangle* tris = (const RefTriangle*)s->tris;
+    const RefNode* nodes = (const RefNode*)s->nodes;
+    for (uint32_t k = 0; k < s->n_nodes; k++) {
+        const RefNode& nd = nodes[k];
+        bool ok = nd.nTris > 0 ? ((uint32_t)nd.offset + (uint32_t)nd.nTris <= s->n_tris)
+                               : (nd.offset > (int32_t)k && (uint32_t)nd.offset < s->n_nodes && k + 1 < s->n_nodes);
+        if (!ok) return (fail(CRT_ERR_INVALID, "scene: BVH node %u is malformed", k));
+    }
+    if (s->n_lights == 0 || !s->light_indices || !(s->lights_area > 0.f))
+        return fail(CRT_ERR_INVALID, "scene: no emissive triangles (the reference divides by a zero light area and indexes an empty "
+                                     "light list in that case, SURVEY.md D13)");
+    for (uint32_t k = 0; k < s->n_lights; k++)
+        if (s->light_indices[k] >= s->n_tris) return (fail(CRT_ERR_INVALID, "scene: light index out of range"));
+    // Fingerprint of everything the derived arrays depend on: geometry, BVH, lights, the flags that pick the trees, and
+    // the camera position / aperture (the tight tree's region of valid ray origins contains the eye).
+    const RefCamera* cam_in = (const RefCamera*)s->camera;
+    Fingerprint fp;
+    {
+        const uint32_t hdr[6] = {s->n_tris, s->n_nodes, s->n_lights,
+                                 c->flags & (CRT_FLAG_REFERENCE_TOPOLOGY | CRT_FLAG_NO_TIGHT_BVH | CRT_FLAG_EXACT_VISIT | CRT_FLAG_TIGHT_BVH |
+                                            CRT_FLAG_DYNAMIC_PAD | CRT_FLAG_STATIC_PAD),
+                                 (uint32_t)sizeof(RefTriangle), (uint32_t)sizeof(RefNode)};
+        fingerprint_mix(fp, hdr, sizeof hdr);
+        const float eye[4] = {cam_in->eye.x, cam_in->eye.y, cam_in->eye.z, cam_in->apertureWidth};
+        fingerprint_mix(fp, eye, sizeof eye);
+        fingerprint_mix(fp, s->light_indices, sizeof(uint32_t) * (size_t)s->n_lights);
+        fingerprint_mix(fp, nodes, sizeof(RefNode) * (size_t)s->n_nodes);
+        fingerprint_mix(fp, tris, sizeof(RefTriangle) * (size_t)s->n_tris);
+    }
+    HostSceneCache& hc = c->host_scene;
+    if (!(hc.valid && hc.fp == fp)) {
+        const int rc_derive = derive_host_scene(c, s, fp);
+        if (rc_derive != CRT_OK) return rc_derive;
     }
     c->wide_stats = hc.wide_stats;
     c->tight_split = hc.tight_split;
