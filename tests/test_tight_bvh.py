@@ -124,3 +124,16 @@ def test_degenerate_and_huge_triangles_keep_their_reference_leaf_box(golden):
     ext = boxes[:, 3:] - boxes[:, :3]
     assert np.all(ext[3] < 0.1) and np.all(ext[3] > 1e-3)            # a tiny triangle keeps a tiny (but padded) box
     assert n_split >= 1
+
+
+def test_pad_mode_is_chosen_by_the_size_of_the_baked_in_pad(golden):
+    """build_tight_bvh's auto rule (host_scene.cpp): dynamic pad when the baked-in pad averages more than 0.3 of the
+    triangle's longest edge - the coarse terrain (pad = 8 edges) and the hand-written scenes - static where the pad is a few
+    per cent of the triangles (the three bundled scenes; measured: profiles/r01z_pad_ab.txt)."""
+    from cudart_b200.scenebuild import PAD_AUTO, tight_bvh
+    want = {"cornell": False, "cornellSphere": False, "monkeys": True, "terrain64": True, "tiny": True, "soup": True}
+    for name, dynamic in want.items():
+        fs, _ = golden(name)
+        lo, hi = region_of(fs)
+        _, _, _, dyn = tight_bvh(fs.tris, fs.nodes, lo, hi, pad_mode=PAD_AUTO, pads=True)
+        assert dyn == dynamic, name
