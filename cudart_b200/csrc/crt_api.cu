@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -66,7 +67,7 @@ struct Fingerprint {
     uint64_t a = 0, b = 0;
     bool operator==(const Fingerprint& o) const { return a == o.a && b == o.b; }
 };
-void fingerprint_mix(Fingerprint& fp, const void* data, size_t bytes) {
+void fingerprint_mix_serial(Fingerprint& fp, const void* data, size_t bytes) {
     const unsigned char* p = (const unsigned char*)data;
     uint64_t ha[4] = {fp.a ^ bytes, 0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull};
     uint64_t hb[4] = {fp.b + bytes, 0x082EFA98EC4E6C89ull, 0x452821E638D01377ull, 0xBE5466CF34E90C6Cull};
@@ -87,6 +88,29 @@ void fingerprint_mix(Fingerprint& fp, const void* data, size_t bytes) {
     }
     fp.a = ((ha[0] * 3 + ha[1]) * 5 + ha[2]) * 7 + ha[3];
     fp.b = ((hb[0] * 11 + hb[1]) * 13 + hb[2]) * 17 + hb[3];
+}
+// Large arrays are hashed in fixed 4 MB chunks on the host's threads and the chunk hashes folded in order, so the value
+// does not depend on the number of threads (one thread: 40 ms for the 155 MB of a 999 700-triangle scene, i.e. most of
+// what crt_update_scene costs per frame once nothing has to be rebuilt).
+void fingerprint_mix(Fingerprint& fp, const void* data, size_t bytes) {
+    constexpr size_t kChunk = 4u << 20;
+    if (bytes <= 2 * kChunk) { fingerprint_mix_serial(fp, data, bytes); return; }
+    const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
+    std::vector<Fingerprint> part(n_chunks);
+    std::atomic<size_t> next{0};
+    auto work = [&] {
+        for (size_t c; (c = next.fetch_add(1)) < n_chunks;) {
+            part[c].a = c;
+            part[c].b = ~c;
+            fingerprint_mix_serial(part[c], (const unsigned char*)data + c * kChunk, std::min(kChunk, bytes - c * kChunk));
+        }
+    };
+    const size_t n_threads = std::min<size_t>(std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())), n_chunks);
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < n_threads; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    fingerprint_mix_serial(fp, part.data(), n_chunks * sizeof(Fingerprint));
 }
 
 // What upload_scene derives from the caller's triangles and BVH nodes on the host.  Kept per context so that
@@ -763,6 +787,15 @@ int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t
         if (!tb.nodes.empty()) flatten_wide(tb.nodes.data(), (uint32_t)tb.nodes.size(), tb.tris.data(), n_tris, tw);
         *n_wide_out = (uint32_t)tw.size();
     }
+    return CRT_OK;
+}
+
+int crt_fingerprint(const void* data, size_t bytes, uint64_t out[2]) {
+    if ((!data && bytes) || !out) return fail(CRT_ERR_INVALID, "crt_fingerprint: null argument");
+    Fingerprint fp;
+    fingerprint_mix(fp, data, bytes);
+    out[0] = fp.a;
+    out[1] = fp.b;
     return CRT_OK;
 }
 

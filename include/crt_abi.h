@@ -123,6 +123,8 @@ int crt_reset(crt_ctx* ctx);                                  /* zero accumulato
  * The arrays derived on the host (4-ary trees, triangle records) are kept per context and only rebuilt when the
  * triangles, BVH nodes, light list or camera position differ from the previous call; they are uploaded every call. */
 int crt_update_scene(crt_ctx* ctx, const crt_scene_desc* scene);
+/* The 128-bit fingerprint crt_update_scene compares (host only, no device needed): introspection for tests. */
+int crt_fingerprint(const void* data, size_t bytes, uint64_t out[2]);
 /* How often this context rebuilt its derived host arrays, how often it uploaded a scene, and the host -> device bytes
  * of the last upload. */
 int crt_scene_info(const crt_ctx* ctx, uint64_t* host_rebuilds_out, uint64_t* uploads_out, uint64_t* last_upload_bytes_out);

@@ -92,3 +92,32 @@ def test_two_rank_gloo_gather_reassembles_the_framebuffer(tmp_path):
     script.write_text(WORKER % {"root": ROOT, "port": port})
     procs = [subprocess.Popen([sys.executable, str(script), str(r)]) for r in range(2)]
     assert [p.wait(timeout=120) for p in procs] == [0, 0]
+
+
+def test_scene_fingerprint_sees_every_byte():
+    """crt_update_scene rebuilds its derived arrays iff this fingerprint of the caller's arrays changes (crt_api.cu):
+    deterministic, and a single flipped bit anywhere - first byte, a 4 MB chunk seam of the threaded path, the ragged tail -
+    changes it."""
+    import ctypes as C
+    from cudart_b200 import capi
+    lib = capi.lib()
+
+    def fp(a):
+        out = (C.c_uint64 * 2)()
+        capi.check(lib.crt_fingerprint(a.ctypes.data, a.nbytes, C.byref(out)))
+        return (int(out[0]), int(out[1]))
+
+    rng = np.random.default_rng(7)
+    for nbytes in (1, 31, 32, 33, 4096 + 5, (9 << 20) + 13):          # the last one takes the chunked, threaded path
+        a = rng.integers(0, 256, nbytes, dtype=np.uint8)
+        base = fp(a)
+        assert base == fp(a.copy())
+        seen = {base}
+        for pos in sorted({0, nbytes // 2, nbytes - 1, min(nbytes - 1, (4 << 20) - 1), min(nbytes - 1, 4 << 20), min(nbytes - 1, 8 << 20)}):
+            b = a.copy()
+            b[pos] ^= 1
+            seen.add(fp(b))
+            assert fp(b) != base, (nbytes, pos)
+        assert len(seen) >= 2
+        assert fp(a[:-1]) != base if nbytes > 1 else True           # the length is part of it
+    assert fp(np.zeros(64, np.uint8)) != fp(np.zeros(65, np.uint8))
