@@ -161,7 +161,8 @@ struct crt_ctx {
     DevBuf<float> tex_data;
     // wave
     DevBuf<float4> rq_o[2], rq_d[2], hits, sq_o, sq_d, sq_c, st_mask, color;
-    DevBuf<uint32_t> rq_path[2], sq_path, st_key;
+    DevBuf<uint32_t> rq_path[2], sq_path;
+    DevBuf<uint2> st_key;
     DevBuf<DCounters> counters;
     DevBuf<DStats> stats;
     DevBuf<float4> accum;

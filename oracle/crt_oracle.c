@@ -9,6 +9,7 @@
  */
 #include "crt_oracle.h"
 #include "../include/crt_rng.h"
+#include "../include/crt_math.h"
 
 #include <float.h>
 #include <math.h>
@@ -65,7 +66,7 @@ static inline f2 add2(f2 a, f2 b) { f2 r = {a.x + b.x, a.y + b.y}; return r; }
 static inline f2 mul2f(f2 a, float b) { f2 r = {a.x * b, a.y * b}; return r; }
 
 /* ---- Sampler (renderer.cu:72-78) ----------------------------------------------------------- */
-typedef struct { int mode; uint32_t key, dim; } Sampler;
+typedef struct { int mode; crt_rng_key_t key; uint32_t dim; } Sampler;
 static inline float nextFloat(Sampler* s) {
     if (s->mode == ORC_RNG_RAND) return rand() / (float)RAND_MAX;
     return crt_rng_uniform(s->key, s->dim++);
@@ -73,6 +74,16 @@ static inline float nextFloat(Sampler* s) {
 float orc_counter_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t dim) {
     return crt_rng_uniform(crt_rng_key(seed, pixel, sample), dim);
 }
+uint32_t orc_counter_bits(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t dim) {
+    return crt_rng_bits(crt_rng_key(seed, pixel, sample), dim);
+}
+/* cosf/sinf of the reference (renderer.cu:384, camera.cu:48-49).  The rand() mode is the reference as it stands (libm);
+ * the replay mode evaluates the product's own function (include/crt_math.h) so that both sides round identically. */
+static inline void sinCos(const Sampler* s, float a, float* sn, float* cs) {
+    if (s->mode == ORC_RNG_RAND) { *cs = cosf(a); *sn = sinf(a); }
+    else crt_sincosf(a, sn, cs);
+}
+void orc_sincos(float a, float* sn, float* cs) { crt_sincosf(a, sn, cs); }
 
 /* ---- Triangle (geometry.cu:38-81) ----------------------------------------------------------- */
 static float triIntersect(const Tri* tr, const Ray* r, float* o_u, float* o_v) {
@@ -267,8 +278,10 @@ static Ray computeCameraRay(const Cam* cam, int i, int j, Sampler* s) {
         /* `rand - 0.5f * 2 * M_PI`: (0.5f*2) is float 1.0f, times M_PI in double, float minus double */
         float r1 = (float)((double)nextFloat(s) - (double)(0.5f * 2) * M_PI);
         float r2 = nextFloat(s) - 0.5f;
-        rightJitter = cosf(r1) * r2 * cam->apertureWidth;
-        upJitter = sinf(r1) * r2 * cam->apertureWidth;
+        float sn, cs;
+        sinCos(s, r1, &sn, &cs);
+        rightJitter = cs * r2 * cam->apertureWidth;
+        upJitter = sn * r2 * cam->apertureWidth;
         origin = add3(origin, add3(mulf(cam->right, rightJitter), mulf(cam->up, upJitter)));
         f3 focalPoint = add3(cam->eye, mulf(direction, cam->focusDistance));
         direction = sub3(focalPoint, origin);
@@ -316,7 +329,9 @@ static f3 sampleDiffuseBSDF(const orc_scene* s, SurfaceInteraction* si, const Tr
     f3 w = si->normal;
     f3 u = normalize3(cross3((fabsf(w.x) > 0.1f ? mk3(0.f, 1.f, 0.f) : mk3(1.f, 0.f, 0.f)), w));
     f3 v = cross3(w, u);
-    si->inputDirection = normalize3(add3(add3(mulf(mulf(u, cosf(r1)), r2sq), mulf(mulf(v, sinf(r1)), r2sq)), mulf(w, sqrtf(1.f - r2))));
+    float sn, cs;
+    sinCos(smp, r1, &sn, &cs);
+    si->inputDirection = normalize3(add3(add3(mulf(mulf(u, cs), r2sq), mulf(mulf(v, sn), r2sq)), mulf(w, sqrtf(1.f - r2))));
     si->pdf = 0.5f;
     float cosineWeight = dot3(si->inputDirection, si->normal);
     f3 kd = diffuseColor;
@@ -500,7 +515,7 @@ int orc_render_accum(const orc_scene* s, uint32_t W, uint32_t H, uint32_t first_
     if (row1 > H) row1 = H;
     if (rng_mode == ORC_RNG_RAND || threads <= 1 || ray_log) {
         Ctx cx = {s, c, ray_log, ray_log_cap, 0};
-        Sampler smp = {rng_mode, 0, 0};
+        Sampler smp = {rng_mode, {0, 0}, 0};
         for (uint32_t sm = 0; sm < spp; sm++)
             for (uint32_t x = 0; x < W; x++)
                 for (uint32_t y = row0; y < row1; y++) {

@@ -49,7 +49,9 @@ class Counters(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the C restatement (and, where /root/reference exists, oracle/_ref)."""
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "crt_oracle.c")):
+    srcs = [os.path.join(_HERE, "crt_oracle.c"), os.path.join(_HERE, "crt_oracle.h"),
+            os.path.join(_HERE, "..", "include", "crt_rng.h"), os.path.join(_HERE, "..", "include", "crt_math.h")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "oracle"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
@@ -70,6 +72,10 @@ def lib():
         L.orc_resolve_rgba8.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_counter_uniform.argtypes = [C.c_uint32] * 4
         L.orc_counter_uniform.restype = C.c_float
+        L.orc_counter_bits.argtypes = [C.c_uint32] * 4
+        L.orc_counter_bits.restype = C.c_uint32
+        L.orc_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.orc_sincos.restype = None
         L.srand.argtypes = [C.c_uint]
         _lib = L
     return _lib
@@ -139,3 +145,14 @@ def resolve_rgba8(accum, spp):
 
 def counter_uniform(seed, pixel, sample, dim):
     return float(lib().orc_counter_uniform(seed, pixel, sample, dim))
+
+
+def counter_bits(seed, pixel, sample, dim):
+    return int(lib().orc_counter_bits(seed, pixel, sample, dim))
+
+
+def sincos(a):
+    """(sin, cos) of the product's own function (include/crt_math.h)."""
+    s, c = C.c_float(0), C.c_float(0)
+    lib().orc_sincos(float(a), C.byref(s), C.byref(c))
+    return float(s.value), float(c.value)
