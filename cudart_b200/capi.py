@@ -39,7 +39,7 @@ class Options(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("rank", C.c_uint32), ("world", C.c_uint32),
         ("tile_rows", C.c_uint32), ("seed", C.c_uint32), ("spp_per_wave", C.c_uint32), ("flags", C.c_uint32),
-        ("stream", C.c_void_p),
+        ("stream", C.c_void_p), ("waves_in_flight", C.c_uint32),
     ]
 
 
@@ -63,6 +63,7 @@ SYMBOLS = {
     "crt_create": (C.c_int, [C.POINTER(SceneDesc), C.c_uint32, C.c_uint32, C.POINTER(Options), C.POINTER(C.c_void_p)]),
     "crt_destroy": (None, [C.c_void_p]),
     "crt_render": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "crt_flush": (C.c_int, [C.c_void_p]),
     "crt_sync": (C.c_int, [C.c_void_p]),
     "crt_samples_rendered": (C.c_uint32, [C.c_void_p]),
     "crt_resolve_rgba8": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -75,6 +76,10 @@ SYMBOLS = {
     "crt_trace_closest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]),
     "crt_accum_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "crt_resolve_gathered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crt_resolve_local_rgba8_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "crt_assemble_rgba8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crt_stream_wait_ctx": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "crt_ctx_wait_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "crt_build_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]),
     "crt_build_lights": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                    C.POINTER(C.c_uint32), C.POINTER(C.c_float)]),

@@ -12,7 +12,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <memory>
 #include <new>
 #include <string>
 #include <thread>
@@ -36,6 +39,21 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     g_err = buf;
     return code;
+}
+
+// No exception crosses the C boundary (crt_abi.h): every extern "C" body that allocates, spawns threads or calls into the
+// host scene builders runs inside guarded().
+template <class F>
+int guarded(const char* what, F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(CRT_ERR_NOMEM, "%s: out of host memory", what);
+    } catch (const std::exception& e) {
+        return fail(CRT_ERR_INVALID, "%s: %s", what, e.what());
+    } catch (...) {
+        return fail(CRT_ERR_INVALID, "%s: unknown exception", what);
+    }
 }
 
 #define CU(call)                                                                                      \
@@ -106,10 +124,10 @@ void fingerprint_mix(Fingerprint& fp, const void* data, size_t bytes) {
         }
     };
     const size_t n_threads = std::min<size_t>(std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())), n_chunks);
-    std::vector<std::thread> th;
-    for (size_t t = 1; t < n_threads; t++) th.emplace_back(work);
+    std::vector<std::unique_ptr<Worker>> th;
+    for (size_t t = 1; t < n_threads; t++) th.emplace_back(new Worker(work));
     work();
-    for (auto& t : th) t.join();
+    for (auto& t : th) t->join();
     fingerprint_mix_serial(fp, part.data(), n_chunks * sizeof(Fingerprint));
 }
 
@@ -140,17 +158,42 @@ struct HostSceneCache {
 
 }  // namespace
 
+// One wavefront's worth of path state.  A context has one or two (crt_options.waves_in_flight): with two, consecutive
+// waves run on two streams so that the latency-bound shade launches of one wave can fill the issue slots and launch
+// tails the traversal of the other leaves idle.
+struct WaveSlot {
+    DevBuf<float4> rq_o[2], rq_d[2], hits, sq_o, sq_d, sq_c, st_mask, color;
+    DevBuf<uint32_t> rq_path[2], sq_path;
+    DevBuf<uint2> st_key;
+    DevBuf<DCounters> counters;
+    DWave wv{};
+    LaunchCfg cfg{};
+    cudaEvent_t accumulated = nullptr;       // recorded after this slot's k_accumulate: the next wave's accumulate waits for it
+    void release() {
+        for (int i = 0; i < 2; i++) { rq_o[i].release(); rq_d[i].release(); rq_path[i].release(); }
+        hits.release(); sq_o.release(); sq_d.release(); sq_c.release(); st_mask.release(); color.release();
+        sq_path.release(); st_key.release(); counters.release();
+        if (accumulated) cudaEventDestroy(accumulated);
+        accumulated = nullptr;
+    }
+};
+
 struct crt_ctx {
     int device = 0;
     bool own_stream = false;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr;           // the context's stream: everything a caller can observe is ordered on it
+    cudaStream_t aux_stream = nullptr;       // second wave in flight (forked from / joined into `stream` inside crt_render)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_order = nullptr;
+    std::vector<cudaEvent_t> event_pool;     // timing events are recycled, never created per call
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;   // render spans not yet folded into render_ms
     LaunchCfg cfg{};
-    uint32_t flags = 0, seed = 1234, spp_per_wave = 1, samples = 0;
+    uint32_t flags = 0, seed = 1234, spp_per_wave = 1;
+    uint32_t samples = 0;                    // what Renderer::getSamplesRendered presents: samples asked for so far
+    uint32_t launched = 0;                   // samples whose waves are already enqueued (samples - launched are deferred)
+    uint32_t n_slots = 1, next_slot = 0;
     DScene sc{};
     DTiling tl{};
-    DWave wv{};
+    WaveSlot slot[2];
     WideStats wide_stats{};
     HostSceneCache host_scene;
     uint64_t scene_rebuilds = 0, scene_uploads = 0, scene_upload_bytes = 0;
@@ -159,21 +202,24 @@ struct crt_ctx {
     uint32_t tight_split = 0, tight_nodes = 0;
     DevBuf<uint32_t> lights, tex_dims, tex_offsets;
     DevBuf<float> tex_data;
-    // wave
-    DevBuf<float4> rq_o[2], rq_d[2], hits, sq_o, sq_d, sq_c, st_mask, color;
-    DevBuf<uint32_t> rq_path[2], sq_path;
-    DevBuf<uint2> st_key;
-    DevBuf<DCounters> counters;
     DevBuf<DStats> stats;
     DevBuf<float4> accum;
     DevBuf<uint8_t> gamma_lut;
     // scratch for resolve / trace
-    DevBuf<uchar4> rgba;
+    DevBuf<uchar4> rgba, rgba_local;
     DevBuf<float> f32;
     DevBuf<uint32_t> head;
     uint64_t launches = 0;
     double render_ms = 0;
     double stage_ms[CRT_STAGE_COUNT] = {0};
+
+    cudaEvent_t take_event() {
+        if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void give_event(cudaEvent_t e) { if (e) event_pool.push_back(e); }
 };
 
 namespace {
@@ -191,16 +237,23 @@ int upload(DevBuf<T>& b, const void* src, size_t count, cudaStream_t s) {
 void free_all(crt_ctx* c) {
     cudaSetDevice(c->device);
     c->host_scene.unpin();
-    c->wide.release(); c->tri_isect.release(); c->tri_shade.release(); c->mats.release();
+    c->wide.release(); c->tri_isect.release(); c->tri_shade.release(); c->tri_tight.release(); c->mats.release();
     c->lights.release(); c->light_boxes.release(); c->tex_dims.release(); c->tex_offsets.release(); c->tex_data.release();
-    for (int i = 0; i < 2; i++) { c->rq_o[i].release(); c->rq_d[i].release(); c->rq_path[i].release(); }
-    c->hits.release(); c->sq_o.release(); c->sq_d.release(); c->sq_c.release(); c->st_mask.release(); c->color.release();
-    c->sq_path.release(); c->st_key.release(); c->counters.release(); c->stats.release(); c->accum.release();
-    c->gamma_lut.release(); c->rgba.release(); c->f32.release(); c->head.release();
+    for (WaveSlot& w : c->slot) w.release();
+    c->stats.release(); c->accum.release();
+    c->gamma_lut.release(); c->rgba.release(); c->rgba_local.release(); c->f32.release(); c->head.release();
     for (auto& pr : c->pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
+    c->pending.clear();
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    c->event_pool.clear();
+    for (cudaEvent_t* e : {&c->ev0, &c->ev1, &c->ev_fork, &c->ev_join, &c->ev_order}) {
+        if (*e) cudaEventDestroy(*e);
+        *e = nullptr;
+    }
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    c->aux_stream = nullptr;
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = nullptr;
 }
 
 int check_kernel(const char* what) {
@@ -224,7 +277,7 @@ static int derive_host_scene(crt_ctx* c, const crt_scene_desc* s, const Fingerpr
     std::vector<WideNode>& wide = hc.wide;
     wide.clear();
     std::vector<RefNode> ref_tree;          // the binary tree behind `wide`, for the cost comparison below
-    std::thread ref_job([&] {
+    Worker ref_job([&] {
         std::vector<RefNode> clustered;
         if (!(c->flags & CRT_FLAG_REFERENCE_TOPOLOGY)) recluster_leaves(nodes, s->n_nodes, clustered);
         hc.wide_stats = clustered.empty() ? flatten_wide(nodes, s->n_nodes, tris, s->n_tris, wide)
@@ -233,8 +286,7 @@ static int derive_host_scene(crt_ctx* c, const crt_scene_desc* s, const Fingerpr
     });
     std::vector<TriIsect>& isect = hc.isect;
     std::vector<TriShade>& shade = hc.shade;
-    std::thread rec_job([&] { make_tri_records(tris, s->n_tris, nodes, s->n_nodes, isect, shade); });
-    struct Joiner { std::thread &a, &b; ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); } } joiner{ref_job, rec_job};
+    Worker rec_job([&] { make_tri_records(tris, s->n_tris, nodes, s->n_nodes, isect, shade); });
     // ---- tight per-triangle BVH in front of the reference-leaf tree (host_scene.h) ----
     TightBvh tight;
     F3 region_lo{FLT_MAX, FLT_MAX, FLT_MAX}, region_hi{-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -305,7 +357,8 @@ static int derive_host_scene(crt_ctx* c, const crt_scene_desc* s, const Fingerpr
         for (uint32_t j = 0; j < s->n_nodes; j++)
             if (nodes[j].nTris > 0) leaf_of_first[(uint32_t)nodes[j].offset] = j;
         for (uint32_t k = 0; k < s->n_lights; k++) {
-            const uint32_t j = leaf_of_first[isect[s->light_indices[k]].leafFirst];
+            const uint32_t lf = isect[s->light_indices[k]].leafFirst;
+            const uint32_t j = lf < s->n_tris ? leaf_of_first[lf] : 0xffffffffu;
             if (j == 0xffffffffu) return (fail(CRT_ERR_INVALID, "scene: light %u is in no BVH leaf", k));
             hc.light_boxes[2 * k] = make_float4(nodes[j].mn.x, nodes[j].mn.y, nodes[j].mn.z, 0.f);
             hc.light_boxes[2 * k + 1] = make_float4(nodes[j].mx.x, nodes[j].mx.y, nodes[j].mx.z, 0.f);
@@ -333,8 +386,8 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     const RefNode* nodes = (const RefNode*)s->nodes;
     for (uint32_t k = 0; k < s->n_nodes; k++) {
         const RefNode& nd = nodes[k];
-        bool ok = nd.nTris > 0 ? ((uint32_t)nd.offset + (uint32_t)nd.nTris <= s->n_tris)
-                               : (nd.offset > (int32_t)k && (uint32_t)nd.offset < s->n_nodes && k + 1 < s->n_nodes);
+        bool ok = nd.nTris > 0 ? (nd.offset >= 0 && (int64_t)nd.offset + (int64_t)nd.nTris <= (int64_t)s->n_tris)
+                               : (nd.nTris == 0 && nd.offset > (int32_t)k && (uint32_t)nd.offset < s->n_nodes && k + 1 < s->n_nodes);
         if (!ok) return (fail(CRT_ERR_INVALID, "scene: BVH node %u is malformed", k));
     }
     if (s->n_lights == 0 || !s->light_indices || !(s->lights_area > 0.f))
@@ -342,6 +395,10 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
                                      "light list in that case, SURVEY.md D13)");
     for (uint32_t k = 0; k < s->n_lights; k++)
         if (s->light_indices[k] >= s->n_tris) return (fail(CRT_ERR_INVALID, "scene: light index out of range"));
+    if (s->n_mats == 0 || !s->mat_floats || !s->mat_indices)
+        return fail(CRT_ERR_INVALID, "scene: no materials (every triangle indexes the material table, renderer.cu:154-157)");
+    if (s->n_tex && (!s->tex_dims || !s->tex_offsets || (s->tex_texels && !s->tex_data)))
+        return fail(CRT_ERR_INVALID, "scene: %u textures but null texture arrays", s->n_tex);
     // Fingerprint of everything the derived arrays depend on: geometry, BVH, lights, the flags that pick the trees, and
     // the camera position / aperture (the tight tree's region of valid ray origins contains the eye).
     const RefCamera* cam_in = (const RefCamera*)s->camera;
@@ -368,14 +425,15 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     c->tight_nodes = hc.n_tight_wide;
     const uint32_t n_tight_wide = hc.n_tight_wide;
     for (uint32_t i = 0; i < s->n_tris; i++)
-        if (tris[i].materialId >= std::max(s->n_mats, 1u)) return (fail(CRT_ERR_INVALID, "scene: triangle %u has material %u of %u", i, tris[i].materialId, s->n_mats));
-    std::vector<float4> mats(4 * (size_t)std::max(s->n_mats, 1u));
+        if (tris[i].materialId >= s->n_mats) return (fail(CRT_ERR_INVALID, "scene: triangle %u has material %u of %u", i, tris[i].materialId, s->n_mats));
+    std::vector<float4> mats(4 * (size_t)s->n_mats);
     for (uint32_t m = 0; m < s->n_mats; m++) {
         const float* f = s->mat_floats + 12 * (size_t)m;
         float bs, tx;
         memcpy(&bs, &s->mat_indices[2 * m], 4);
         memcpy(&tx, &s->mat_indices[2 * m + 1], 4);
-        if (s->mat_indices[2 * m + 1] >= (int32_t)s->n_tex) return (fail(CRT_ERR_INVALID, "scene: material %u texture index out of range", m));
+        if (s->mat_indices[2 * m + 1] >= (int32_t)s->n_tex || s->mat_indices[2 * m + 1] < -1)
+            return (fail(CRT_ERR_INVALID, "scene: material %u texture index %d out of range", m, s->mat_indices[2 * m + 1]));
         mats[4 * m + 0] = make_float4(f[0], f[1], f[2], bs);
         mats[4 * m + 1] = make_float4(f[3], f[4], f[5], tx);
         mats[4 * m + 2] = make_float4(f[6], f[7], f[8], 0.f);
@@ -435,8 +493,8 @@ extern "C" {
 int crt_abi_version(void) { return CRT_ABI_VERSION; }
 const char* crt_last_error(void) { return g_err.c_str(); }
 
-int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_options* opt, crt_ctx** out) {
-    if (!s || !out || !W || !H) return fail(CRT_ERR_INVALID, "crt_create: null scene/out or empty image");
+static int create_impl(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_options* opt, crt_ctx*& c) {
+    if (!W || !H) return fail(CRT_ERR_INVALID, "crt_create: null scene/out or empty image");
     if (!s->tris || !s->nodes || !s->n_tris || !s->n_nodes || !s->camera) return fail(CRT_ERR_INVALID, "crt_create: empty scene");
     if (s->n_mats > 128) return fail(CRT_ERR_LIMIT, "crt_create: %u materials > MAX_MATERIALS 128 (renderer.h:22)", s->n_mats);
     if (s->n_tris >= kMaxTris) return fail(CRT_ERR_LIMIT, "crt_create: %u triangles >= %u", s->n_tris, kMaxTris);
@@ -449,6 +507,9 @@ int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_option
     if (o.rank >= o.world) return fail(CRT_ERR_INVALID, "crt_create: rank %u >= world %u", o.rank, o.world);
     if (o.tile_rows == 0) o.tile_rows = 8;
     if (o.seed == 0) o.seed = 1234;
+    if (const char* e = getenv("CRT_WAVES_IN_FLIGHT")) { if (!o.waves_in_flight) o.waves_in_flight = (uint32_t)atoi(e); }   // A/B measurements
+    if (o.waves_in_flight == 0) o.waves_in_flight = 1;
+    if (o.waves_in_flight > 2) return fail(CRT_ERR_INVALID, "crt_create: waves_in_flight %u (1 or 2)", o.waves_in_flight);
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -462,24 +523,27 @@ int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_option
     CU(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) return fail(CRT_ERR_CUDA, "crt_create: device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
 
-    crt_ctx* c = new (std::nothrow) crt_ctx();
-    if (!c) return fail(CRT_ERR_NOMEM, "crt_create: out of host memory");
+    c = new crt_ctx();
     c->device = dev;
     c->flags = o.flags;
     c->seed = o.seed;
-    auto bail = [&](int code) { free_all(c); delete c; return code; };
+    c->n_slots = o.waves_in_flight;
     if (o.stream) c->stream = (cudaStream_t)o.stream;
     else {
-        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(CRT_ERR_CUDA, "cudaStreamCreate failed"));
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
-    cudaEventCreate(&c->ev0);
-    cudaEventCreate(&c->ev1);
-    if (configure_kernels() != 0) return bail(fail(CRT_ERR_CUDA, "crt_create: cannot opt in to %u KB of shared memory per CTA", 56u));
+    if (c->n_slots > 1) CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    for (cudaEvent_t* ev : {&c->ev_fork, &c->ev_join, &c->ev_order}) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    if (configure_kernels() != 0) return fail(CRT_ERR_CUDA, "crt_create: cannot opt in to %u KB of shared memory per CTA", 56u);
     c->cfg.sms = prop.multiProcessorCount;
     c->cfg.stream = c->stream;
+    c->cfg.trav_blocks = 0;
+    if (const char* e = getenv("CRT_TRAV_BLOCKS")) c->cfg.trav_blocks = atoi(e);       // A/B measurements: traversal CTAs per SM
 
-    { const int rc_scene = upload_scene(c, s, W, H); if (rc_scene != CRT_OK) return bail(rc_scene); }
+    { const int rc_scene = upload_scene(c, s, W, H); if (rc_scene != CRT_OK) return rc_scene; }
 
     // ---- pixel ownership ----
     DTiling& tl = c->tl;
@@ -493,34 +557,51 @@ int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_option
 
     // ---- wave buffers ----
     uint32_t k = o.spp_per_wave;
-    if (k == 0) {       // auto: about 16M paths in flight (~3 GB of wave state; measured +12 % over 4M), within a
-                        // quarter of the free device memory, at least 1 spp
+    if (k == 0) {       // auto: about 16M paths in flight in total (~3 GB of wave state; measured +12 % over 4M), within
+                        // a quarter of the free device memory, at least 1 spp per wave
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const uint64_t by_mem = std::max<uint64_t>(1u << 20, free_b / 4 / 192);
-        const uint64_t target = std::min<uint64_t>(16ull << 20, by_mem);
+        const uint64_t target = std::min<uint64_t>(16ull << 20, by_mem) / c->n_slots;
         k = (uint32_t)std::max<uint64_t>(1, target / std::max<uint32_t>(tl.local_pixels, 1));
         k = std::min<uint32_t>(k, 64);
     }
     c->spp_per_wave = k;
     const size_t cap = std::max<size_t>((size_t)tl.local_pixels * k, 32);
-    if (cap >= (1ull << 31)) return bail(fail(CRT_ERR_LIMIT, "crt_create: %zu paths per wave", cap));
-#define AL(buf, count) if (c->buf.alloc(count) != cudaSuccess) return bail(fail(CRT_ERR_NOMEM, "crt_create: cudaMalloc(%s) failed: %s", #buf, cudaGetErrorString(cudaGetLastError())))
-    for (int i = 0; i < 2; i++) { AL(rq_o[i], cap); AL(rq_d[i], cap); AL(rq_path[i], cap); }
-    AL(hits, cap); AL(sq_o, cap); AL(sq_d, cap); AL(sq_c, cap); AL(sq_path, cap);
-    AL(st_mask, cap); AL(st_key, cap); AL(color, cap);
-    AL(counters, 1); AL(stats, 1); AL(head, 1);
-    AL(accum, tl.padded_pixels);
+    if (cap >= (1ull << 31)) return fail(CRT_ERR_LIMIT, "crt_create: %zu paths per wave", cap);
+#define AL(buf, count) if (buf.alloc(count) != cudaSuccess) return fail(CRT_ERR_NOMEM, "crt_create: cudaMalloc(%s) failed: %s", #buf, cudaGetErrorString(cudaGetLastError()))
+    AL(c->stats, 1); AL(c->head, 1);
+    AL(c->accum, tl.padded_pixels);
+    for (uint32_t si = 0; si < c->n_slots; si++) {
+        WaveSlot& w = c->slot[si];
+        for (int i = 0; i < 2; i++) { AL(w.rq_o[i], cap); AL(w.rq_d[i], cap); AL(w.rq_path[i], cap); }
+        AL(w.hits, cap); AL(w.sq_o, cap); AL(w.sq_d, cap); AL(w.sq_c, cap); AL(w.sq_path, cap);
+        AL(w.st_mask, cap); AL(w.st_key, cap); AL(w.color, cap);
+        AL(w.counters, 1);
+        DWave& wv = w.wv;
+        for (int i = 0; i < 2; i++) { wv.rq_o[i] = w.rq_o[i].p; wv.rq_d[i] = w.rq_d[i].p; wv.rq_path[i] = w.rq_path[i].p; }
+        wv.hits = w.hits.p; wv.sq_o = w.sq_o.p; wv.sq_d = w.sq_d.p; wv.sq_c = w.sq_c.p; wv.sq_path = w.sq_path.p;
+        wv.st_mask = w.st_mask.p; wv.st_key = w.st_key.p; wv.color = w.color.p;
+        wv.counters = w.counters.p; wv.stats = c->stats.p; wv.capacity = (uint32_t)cap;
+        w.cfg = c->cfg;
+        w.cfg.stream = si == 0 ? c->stream : c->aux_stream;
+        CU(cudaEventCreateWithFlags(&w.accumulated, cudaEventDisableTiming));
+    }
 #undef AL
-    DWave& wv = c->wv;
-    for (int i = 0; i < 2; i++) { wv.rq_o[i] = c->rq_o[i].p; wv.rq_d[i] = c->rq_d[i].p; wv.rq_path[i] = c->rq_path[i].p; }
-    wv.hits = c->hits.p; wv.sq_o = c->sq_o.p; wv.sq_d = c->sq_d.p; wv.sq_c = c->sq_c.p; wv.sq_path = c->sq_path.p;
-    wv.st_mask = c->st_mask.p; wv.st_key = c->st_key.p; wv.color = c->color.p;
-    wv.counters = c->counters.p; wv.stats = c->stats.p; wv.capacity = (uint32_t)cap;
-    if (cudaMemsetAsync(c->accum.p, 0, (size_t)tl.padded_pixels * sizeof(float4), c->stream) != cudaSuccess ||
-        cudaMemsetAsync(c->stats.p, 0, sizeof(DStats), c->stream) != cudaSuccess ||
-        cudaStreamSynchronize(c->stream) != cudaSuccess)
-        return bail(fail(CRT_ERR_CUDA, "crt_create: upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+    CU(cudaMemsetAsync(c->accum.p, 0, (size_t)tl.padded_pixels * sizeof(float4), c->stream));
+    CU(cudaMemsetAsync(c->stats.p, 0, sizeof(DStats), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return CRT_OK;
+}
+
+int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_options* opt, crt_ctx** out) {
+    if (!s || !out) return fail(CRT_ERR_INVALID, "crt_create: null scene/out or empty image");
+    crt_ctx* c = nullptr;
+    const int rc = guarded("crt_create", [&] { return create_impl(s, W, H, opt, c); });
+    if (rc != CRT_OK) {
+        if (c) { free_all(c); delete c; }
+        return rc;
+    }
     *out = c;
     return CRT_OK;
 }
@@ -528,52 +609,73 @@ int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_option
 void crt_destroy(crt_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     cudaStreamSynchronize(c->stream);
     free_all(c);
     delete c;
 }
 
-int crt_render(crt_ctx* c, uint32_t spp) {
-    if (!c) return fail(CRT_ERR_INVALID, "crt_render: null ctx");
-    CU(cudaSetDevice(c->device));
-    const bool exact = c->flags & CRT_FLAG_EXACT_VISIT, prof = c->flags & CRT_FLAG_PROFILE, stats = c->flags & CRT_FLAG_STATS;
-    cudaEvent_t a, b;
-    CU(cudaEventCreate(&a));
-    CU(cudaEventCreate(&b));
+// Enqueue the waves of every sample asked for so far (c->launched .. c->samples).  With two wave slots consecutive waves
+// alternate between the context's stream and the auxiliary stream: the auxiliary stream is forked from the context's
+// stream before its first wave and joined back after the last one, and the per-pixel accumulation - the only thing two
+// waves share - is chained in wave order by events, so the sums have the same bits whatever the number of slots.
+static int launch_pending(crt_ctx* c) {
+    const uint32_t spp = c->samples - c->launched;
+    if (spp == 0 || c->tl.local_pixels == 0) { c->launched = c->samples; return CRT_OK; }
+    const bool exact = c->flags & CRT_FLAG_EXACT_VISIT, stats = c->flags & CRT_FLAG_STATS;
+    const bool prof = (c->flags & CRT_FLAG_PROFILE) && c->n_slots == 1;
+    cudaEvent_t a = c->take_event(), b = c->take_event();
     CU(cudaEventRecord(a, c->stream));
     struct Span { int stage; cudaEvent_t e; };
     std::vector<Span> spans;        // CRT_FLAG_PROFILE: an event after every launch; stage -1 opens a wave
     auto mark = [&](int stage) {
         if (!prof) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
+        cudaEvent_t e = c->take_event();
         cudaEventRecord(e, c->stream);
         spans.push_back({stage, e});
     };
+    const uint32_t n_waves = (spp + c->spp_per_wave - 1) / c->spp_per_wave;
+    const bool fork = c->n_slots > 1 && n_waves > 1;
+    if (fork) {
+        CU(cudaEventRecord(c->ev_fork, c->stream));
+        CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    }
     uint32_t done = 0;
-    while (done < spp && c->tl.local_pixels) {
+    WaveSlot* prev = nullptr;
+    uint32_t slot_i = 0;
+    while (done < spp) {
         const uint32_t k = std::min(c->spp_per_wave, spp - done);
-        CU(cudaMemsetAsync(c->counters.p, 0, sizeof(DCounters), c->stream));
+        WaveSlot& w = c->slot[fork ? slot_i : 0];
+        const LaunchCfg& cfg = w.cfg;
+        CU(cudaMemsetAsync(w.counters.p, 0, sizeof(DCounters), cfg.stream));
         mark(-1);
-        launch_raygen(c->sc, c->tl, c->wv, c->samples + done, k, c->seed, c->cfg);
+        launch_raygen(c->sc, c->tl, w.wv, c->launched + done, k, c->seed, cfg);
         mark(CRT_STAGE_RAYGEN);
         // traverse(E0); shade(0); traverse(E1 + S0); shade(1); ... traverse(E5 + S4); shade(5); traverse(S5)
         for (int bounce = 0; bounce < kMaxBounces; bounce++) {
-            launch_traverse(c->sc, c->wv, bounce, bounce - 1, exact, stats, c->cfg);
+            launch_traverse(c->sc, w.wv, bounce, bounce - 1, exact, stats, cfg);
             mark(CRT_STAGE_EXTEND);
-            launch_shade(c->sc, c->tl, c->wv, bounce, c->cfg);
+            launch_shade(c->sc, c->tl, w.wv, bounce, cfg);
             mark(CRT_STAGE_SHADE);
         }
-        launch_traverse(c->sc, c->wv, -1, kMaxBounces - 1, exact, stats, c->cfg);
+        launch_traverse(c->sc, w.wv, -1, kMaxBounces - 1, exact, stats, cfg);
         mark(CRT_STAGE_SHADOW);
-        launch_accumulate(c->tl, c->wv, c->accum.p, k, c->cfg);
+        if (fork && prev) CU(cudaStreamWaitEvent(cfg.stream, prev->accumulated, 0));      // accumulate in wave order
+        launch_accumulate(c->tl, w.wv, c->accum.p, k, cfg);
+        if (fork) CU(cudaEventRecord(w.accumulated, cfg.stream));
         mark(CRT_STAGE_ACCUM);
         c->launches += 3 + 2 * kMaxBounces;
         done += k;
+        prev = &w;
+        slot_i ^= 1u;
+    }
+    if (fork) {
+        CU(cudaEventRecord(c->ev_join, c->aux_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
     CU(cudaEventRecord(b, c->stream));
     c->pending.emplace_back(a, b);
-    c->samples += spp;
+    c->launched = c->samples;
     int rc = check_kernel("render wave");
     if (rc) return rc;
     if (prof) {
@@ -584,20 +686,45 @@ int crt_render(crt_ctx* c, uint32_t spp) {
             cudaEventElapsedTime(&ms, spans[i - 1].e, spans[i].e);
             c->stage_ms[spans[i].stage] += ms;
         }
-        for (auto& sp : spans) cudaEventDestroy(sp.e);
+        for (auto& sp : spans) c->give_event(sp.e);
     }
     return CRT_OK;
 }
 
+int crt_render(crt_ctx* c, uint32_t spp) {
+    if (!c) return fail(CRT_ERR_INVALID, "crt_render: null ctx");
+    return guarded("crt_render", [&] {
+        CU(cudaSetDevice(c->device));
+        if ((uint64_t)c->samples + spp > 0xffffffffull) return fail(CRT_ERR_LIMIT, "crt_render: sample counter overflow");
+        c->samples += spp;
+        // The literal seam renders one sample per call (Renderer::renderOneSamplePerPixel x spp, terminal_launcher.cpp:12-14)
+        // while the machine wants whole wavefront batches: calls that add up to less than one batch are queued here and
+        // launched by the call that completes the batch (or by crt_flush / crt_sync / any read-out).  The presented counter
+        // (crt_samples_rendered) advances with every call; sample indices, and therefore the image, do not depend on how
+        // the samples were grouped into waves.
+        if (c->samples - c->launched < c->spp_per_wave) return (int)CRT_OK;
+        return launch_pending(c);
+    });
+}
+
+int crt_flush(crt_ctx* c) {
+    if (!c) return fail(CRT_ERR_INVALID, "crt_flush: null ctx");
+    return guarded("crt_flush", [&] {
+        CU(cudaSetDevice(c->device));
+        return launch_pending(c);
+    });
+}
+
 int crt_sync(crt_ctx* c) {
     if (!c) return fail(CRT_ERR_INVALID, "crt_sync: null ctx");
-    CU(cudaSetDevice(c->device));
+    int rc = crt_flush(c);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     for (auto& pr : c->pending) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) c->render_ms += ms;
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
+        c->give_event(pr.first);
+        c->give_event(pr.second);
     }
     c->pending.clear();
     return CRT_OK;
@@ -606,7 +733,8 @@ int crt_sync(crt_ctx* c) {
 uint32_t crt_samples_rendered(const crt_ctx* c) { return c ? c->samples : 0; }
 
 static int resolve_common(crt_ctx* c, const float4* src, bool gathered, uint8_t* rgba_dst, float* f32_dst, int f32_mode) {
-    CU(cudaSetDevice(c->device));
+    int rc = crt_flush(c);
+    if (rc) return rc;
     const size_t n = (size_t)c->tl.W * c->tl.H;
     if (rgba_dst && !c->rgba.p) CU(c->rgba.alloc(n));
     if (f32_dst && !c->f32.p) CU(c->f32.alloc(3 * n));
@@ -615,7 +743,7 @@ static int resolve_common(crt_ctx* c, const float4* src, bool gathered, uint8_t*
     launch_resolve(c->tl, src, gathered, std::max(c->samples, 1u), c->gamma_lut.p, rgba_dst ? c->rgba.p : nullptr,
                    f32_dst ? c->f32.p : nullptr, f32_mode, c->cfg);
     c->launches++;
-    int rc = check_kernel("resolve");
+    rc = check_kernel("resolve");
     if (rc) return rc;
     if (rgba_dst) CU(cudaMemcpyAsync(rgba_dst, c->rgba.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (f32_dst) CU(cudaMemcpyAsync(f32_dst, c->f32.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -639,17 +767,67 @@ int crt_resolve_gathered(crt_ctx* c, const void* d_gathered, uint8_t* rgba8_dst,
     return resolve_common(c, (const float4*)d_gathered, true, rgba8_dst, f32_dst, 1);
 }
 
+// ---- multi-GPU read-out in display bytes (4 B per pixel instead of 16) -----------------------------------------------
+int crt_resolve_local_rgba8_device(crt_ctx* c, void** d_ptr, size_t* bytes) {
+    if (!c || !d_ptr) return fail(CRT_ERR_INVALID, "crt_resolve_local_rgba8_device: null argument");
+    int rc = crt_flush(c);
+    if (rc) return rc;
+    CU(c->rgba_local.alloc(std::max<size_t>(c->tl.padded_pixels, 1)));
+    launch_resolve_local(c->tl, c->accum.p, std::max(c->samples, 1u), c->gamma_lut.p, c->rgba_local.p, c->cfg);
+    c->launches++;
+    rc = check_kernel("resolve_local");
+    if (rc) return rc;
+    *d_ptr = c->rgba_local.p;
+    if (bytes) *bytes = (size_t)c->tl.padded_pixels * 4;
+    return CRT_OK;
+}
+
+int crt_assemble_rgba8(crt_ctx* c, const void* d_gathered, uint8_t* dst) {
+    if (!c || !d_gathered || !dst) return fail(CRT_ERR_INVALID, "crt_assemble_rgba8: null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->tl.W * c->tl.H;
+    if (!c->rgba.p) CU(c->rgba.alloc(n));
+    launch_assemble(c->tl, (const uchar4*)d_gathered, c->rgba.p, c->cfg);
+    c->launches++;
+    int rc = check_kernel("assemble");
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dst, c->rgba.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    return crt_sync(c);
+}
+
+// ---- stream ordering against a caller's stream (collectives run there), without host synchronisation ----------------
+int crt_stream_wait_ctx(crt_ctx* c, void* stream) {
+    if (!c) return fail(CRT_ERR_INVALID, "crt_stream_wait_ctx: null ctx");
+    int rc = crt_flush(c);
+    if (rc) return rc;
+    if ((cudaStream_t)stream == c->stream) return CRT_OK;
+    CU(cudaEventRecord(c->ev_order, c->stream));
+    CU(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_order, 0));
+    return CRT_OK;
+}
+int crt_ctx_wait_stream(crt_ctx* c, void* stream) {
+    if (!c) return fail(CRT_ERR_INVALID, "crt_ctx_wait_stream: null ctx");
+    CU(cudaSetDevice(c->device));
+    if ((cudaStream_t)stream == c->stream) return CRT_OK;
+    CU(cudaEventRecord(c->ev_order, (cudaStream_t)stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_order, 0));
+    return CRT_OK;
+}
+
 int crt_update_scene(crt_ctx* c, const crt_scene_desc* s) {
     if (!c || !s) return fail(CRT_ERR_INVALID, "crt_update_scene: null argument");
     if (!s->tris || !s->nodes || !s->n_tris || !s->n_nodes || !s->camera) return fail(CRT_ERR_INVALID, "crt_update_scene: empty scene");
     if (s->n_mats > 128) return fail(CRT_ERR_LIMIT, "crt_update_scene: %u materials > MAX_MATERIALS 128", s->n_mats);
     if (s->n_tris >= kMaxTris) return fail(CRT_ERR_LIMIT, "crt_update_scene: %u triangles >= %u", s->n_tris, kMaxTris);
-    CU(cudaSetDevice(c->device));
-    CU(cudaStreamSynchronize(c->stream));                    // the previous frame may still be reading the old arrays
-    int rc = upload_scene(c, s, c->tl.W, c->tl.H);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(c->stream));                    // host staging vectors die with this call
-    return crt_reset(c);
+    return guarded("crt_update_scene", [&] {
+        CU(cudaSetDevice(c->device));
+        c->samples = c->launched;                                // samples still queued on the host belong to the old scene: dropped
+        CU(cudaStreamSynchronize(c->stream));                    // the previous frame may still be reading the old arrays
+        int rc = upload_scene(c, s, c->tl.W, c->tl.H);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(c->stream));                    // host staging vectors die with this call
+        return crt_reset(c);
+    });
 }
 
 int crt_reset(crt_ctx* c) {
@@ -657,6 +835,7 @@ int crt_reset(crt_ctx* c) {
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(c->accum.p, 0, (size_t)c->tl.padded_pixels * sizeof(float4), c->stream));
     c->samples = 0;
+    c->launched = 0;
     return CRT_OK;
 }
 
@@ -716,6 +895,8 @@ int crt_trace_closest(crt_ctx* c, const crt_ray* rays, size_t n, crt_hit* hits, 
 
 int crt_accum_device_ptr(crt_ctx* c, void** d_ptr, size_t* padded_pixels) {
     if (!c || !d_ptr) return fail(CRT_ERR_INVALID, "crt_accum_device_ptr: null argument");
+    int rc = crt_flush(c);                      // what the caller reads next must already be enqueued
+    if (rc) return rc;
     *d_ptr = c->accum.p;
     if (padded_pixels) *padded_pixels = c->tl.padded_pixels;
     return CRT_OK;
@@ -724,39 +905,41 @@ int crt_accum_device_ptr(crt_ctx* c, void** d_ptr, size_t* padded_pixels) {
 // ---- host scene build ----------------------------------------------------------------------------
 int crt_build_bvh(void* tris, const float* positions, uint32_t n_tris, void* nodes_out, uint32_t* n_nodes_out) {
     if (!tris || !positions || !nodes_out || !n_nodes_out) return fail(CRT_ERR_INVALID, "crt_build_bvh: null argument");
-    try {
+    return guarded("crt_build_bvh", [&] {
         std::vector<RefNode> nodes;
         build_reference_bvh((RefTriangle*)tris, positions, n_tris, nodes);
         memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(RefNode));
         *n_nodes_out = (uint32_t)nodes.size();
-    } catch (const std::bad_alloc&) {
-        return fail(CRT_ERR_NOMEM, "crt_build_bvh: out of memory");
-    }
-    return CRT_OK;
+        return (int)CRT_OK;
+    });
 }
 
 int crt_build_lights(void* tris, uint32_t n_tris, float* mat_floats, const int32_t* mat_indices, uint32_t n_mats,
                      uint32_t* light_indices_out, uint32_t* n_lights_out, float* lights_area_out) {
     if (!tris || !mat_floats || !mat_indices || !light_indices_out || !n_lights_out || !lights_area_out)
         return fail(CRT_ERR_INVALID, "crt_build_lights: null argument");
-    std::vector<uint32_t> lights;
-    float area = 0;
-    build_light_list((RefTriangle*)tris, n_tris, mat_floats, mat_indices, n_mats, lights, area);
-    memcpy(light_indices_out, lights.data(), lights.size() * 4);
-    *n_lights_out = (uint32_t)lights.size();
-    *lights_area_out = area;
-    return CRT_OK;
+    return guarded("crt_build_lights", [&] {
+        std::vector<uint32_t> lights;
+        float area = 0;
+        build_light_list((RefTriangle*)tris, n_tris, mat_floats, mat_indices, n_mats, lights, area);
+        memcpy(light_indices_out, lights.data(), lights.size() * 4);
+        *n_lights_out = (uint32_t)lights.size();
+        *lights_area_out = area;
+        return (int)CRT_OK;
+    });
 }
 
 int crt_wide_bvh(const void* nodes, uint32_t n_nodes, void* wide_out, uint32_t cap, uint32_t* n_wide_out) {
     if (!nodes || !n_wide_out) return fail(CRT_ERR_INVALID, "crt_wide_bvh: null argument");
-    std::vector<WideNode> wide;
-    std::vector<RefNode> clustered;
-    recluster_leaves((const RefNode*)nodes, n_nodes, clustered);
-    flatten_wide(clustered.data(), (uint32_t)clustered.size(), nullptr, 0, wide);
-    *n_wide_out = (uint32_t)wide.size();
-    if (wide_out) memcpy(wide_out, wide.data(), std::min<size_t>(cap, wide.size()) * sizeof(WideNode));
-    return CRT_OK;
+    return guarded("crt_wide_bvh", [&] {
+        std::vector<WideNode> wide;
+        std::vector<RefNode> clustered;
+        recluster_leaves((const RefNode*)nodes, n_nodes, clustered);
+        flatten_wide(clustered.data(), (uint32_t)clustered.size(), nullptr, 0, wide);
+        *n_wide_out = (uint32_t)wide.size();
+        if (wide_out) memcpy(wide_out, wide.data(), std::min<size_t>(cap, wide.size()) * sizeof(WideNode));
+        return (int)CRT_OK;
+    });
 }
 
 
@@ -764,6 +947,7 @@ int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t
                   float* tri_boxes_out, float* tri_pad_out, uint32_t* dynamic_out,
                   uint32_t* n_split_out, uint32_t* n_tight_nodes_out, uint32_t* n_wide_out, double* sah_out) {
     if (!tris || !nodes || !region || pad_mode > 2) return fail(CRT_ERR_INVALID, "crt_tight_bvh: bad argument");
+    return guarded("crt_tight_bvh", [&] {
     TightBvh tb;
     build_tight_bvh((const RefTriangle*)tris, n_tris, (const RefNode*)nodes, n_nodes, F3{region[0], region[1], region[2]},
                     F3{region[3], region[4], region[5]}, (PadMode)pad_mode, tb);
@@ -788,22 +972,25 @@ int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t
         if (!tb.nodes.empty()) flatten_wide(tb.nodes.data(), (uint32_t)tb.nodes.size(), tb.tris.data(), n_tris, tw);
         *n_wide_out = (uint32_t)tw.size();
     }
-    return CRT_OK;
+    return (int)CRT_OK;
+    });
 }
 
 int crt_fingerprint(const void* data, size_t bytes, uint64_t out[2]) {
     if ((!data && bytes) || !out) return fail(CRT_ERR_INVALID, "crt_fingerprint: null argument");
-    Fingerprint fp;
-    fingerprint_mix(fp, data, bytes);
-    out[0] = fp.a;
-    out[1] = fp.b;
-    return CRT_OK;
+    return guarded("crt_fingerprint", [&] {
+        Fingerprint fp;
+        fingerprint_mix(fp, data, bytes);
+        out[0] = fp.a;
+        out[1] = fp.b;
+        return (int)CRT_OK;
+    });
 }
 
 int crt_lane_stats(crt_ctx* c, uint64_t out[8]) {
     if (!c || !out) return fail(CRT_ERR_INVALID, "crt_lane_stats: null argument");
-    CU(cudaSetDevice(c->device));
-    CU(cudaStreamSynchronize(c->stream));
+    int rc = crt_sync(c);
+    if (rc) return rc;
     DStats st;
     CU(cudaMemcpy(&st, c->stats.p, sizeof st, cudaMemcpyDeviceToHost));
     for (int k = 0; k < 8; k++) out[k] = st.lanes[k];

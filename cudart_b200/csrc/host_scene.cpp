@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 
 namespace crt {
 namespace {
@@ -158,7 +159,7 @@ struct Builder {
         }
         int lower, upper;
         if (depth < kForkDepth && n >= fork_min()) {
-            std::thread t([&, this] { lower = build(start, mid, depth + 1); });
+            Worker t([&, this] { lower = build(start, mid, depth + 1); });
             upper = build(mid, end, depth + 1);
             t.join();
         } else {
@@ -634,7 +635,7 @@ struct TightBuilder {
         for (uint32_t i = lo; i < mid; i++) left_weight += prims[i].count;
         uint32_t first, second;
         if (depth < 4 && n >= (1u << 14)) {
-            std::thread t([&, this] { first = build(lo, mid, slot_base, depth + 1); });
+            Worker t([&, this] { first = build(lo, mid, slot_base, depth + 1); });
             second = build(mid, hi, slot_base + left_weight, depth + 1);
             t.join();
         } else {
@@ -655,12 +656,16 @@ void parallel_for(uint32_t n, F fn) {
     const uint32_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     const uint32_t parts = n < (1u << 15) ? 1u : hw;
     if (parts == 1) { fn(0u, n); return; }
-    std::vector<std::thread> th;
+    std::vector<std::unique_ptr<Worker>> th;
     for (uint32_t p = 0; p < parts; p++) {
         const uint32_t b = (uint32_t)((uint64_t)n * p / parts), e = (uint32_t)((uint64_t)n * (p + 1) / parts);
-        th.emplace_back([=, &fn] { fn(b, e); });
+        th.emplace_back(new Worker([=, &fn] { fn(b, e); }));
     }
-    for (auto& t : th) t.join();
+    std::exception_ptr first;
+    for (auto& t : th) {
+        try { t->join(); } catch (...) { if (!first) first = std::current_exception(); }
+    }
+    if (first) std::rethrow_exception(first);
 }
 inline float round_down(double v) { float f = (float)v; return (double)f > v ? std::nextafterf(f, -INFINITY) : f; }
 inline float round_up(double v) { float f = (float)v; return (double)f < v ? std::nextafterf(f, INFINITY) : f; }
@@ -893,7 +898,7 @@ void make_tri_records(const RefTriangle* tris, uint32_t n, const RefNode* nodes,
         a.e2[0] = t.e2.x; a.e2[1] = t.e2.y; a.e2[2] = t.e2.z;
         a.materialId = t.materialId;
         a.index = i;
-        a.leafFirst = 0;
+        a.leafFirst = 0xffffffffu;          // in no reference leaf (never reached by the reference traversal) until shown otherwise
         TriShade& s = shade[i];
         std::memset(&s, 0, sizeof s);
         s.n1[0] = t.n1.x; s.n1[1] = t.n1.y; s.n1[2] = t.n1.z;

@@ -7,9 +7,35 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <exception>
+#include <thread>
+#include <utility>
 #include <vector>
 
 namespace crt {
+
+// A host thread whose body cannot take the process down: an exception thrown inside is carried to join() and rethrown
+// on the joining thread (where the C ABI's guard turns it into an error code).  The destructor joins.
+class Worker {
+    std::thread t_;
+    std::exception_ptr err_;
+public:
+    Worker() = default;
+    template <class F>
+    explicit Worker(F f) {
+        t_ = std::thread([this, f]() mutable {
+            try { f(); } catch (...) { err_ = std::current_exception(); }
+        });
+    }
+    Worker(const Worker&) = delete;
+    Worker& operator=(const Worker&) = delete;
+    bool joinable() const { return t_.joinable(); }
+    void join() {
+        if (t_.joinable()) t_.join();
+        if (err_) { std::exception_ptr e = err_; err_ = nullptr; std::rethrow_exception(e); }
+    }
+    ~Worker() { if (t_.joinable()) t_.join(); }
+};
 
 struct F3 { float x, y, z; };
 struct F2 { float x, y; };

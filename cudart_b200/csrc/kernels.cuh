@@ -75,7 +75,7 @@ struct DWave {
     uint32_t capacity;
 };
 
-struct LaunchCfg { int sms; cudaStream_t stream; };
+struct LaunchCfg { int sms; cudaStream_t stream; int trav_blocks; /* traversal CTAs per SM, 0 = the compiled default */ };
 
 constexpr uint32_t kMaxSmemNodes = 288;        // 36 KB of nodes + 20 KB of stack per CTA, 4 CTAs per SM: 224 of 227 KB
 int configure_kernels();                       // opt the traversal kernels into > 48 KB of dynamic shared memory
@@ -92,4 +92,10 @@ void launch_trace(const DScene& sc, const float4* rays, uint32_t n, float4* hits
 // Resolve: accum is rank-major (world x padded_pixels float4) when gathered, else this rank's compact buffer.
 void launch_resolve(const DTiling& tl, const float4* accum, bool gathered, uint32_t spp, const uint8_t* gamma_lut,
                     uchar4* rgba_out, float* f32_out, int f32_mode /*0 none,1 mean,2 sum*/, const LaunchCfg& cfg);
+// Multi-GPU read-out in display bytes: this rank's owned pixels as RGBA8 in its compact tile-major order
+// (padded_pixels uchar4, identical size on every rank; pad slots zero) ...
+void launch_resolve_local(const DTiling& tl, const float4* accum, uint32_t spp, const uint8_t* gamma_lut, uchar4* rgba_local,
+                          const LaunchCfg& cfg);
+// ... and, on the rank that collected them (rank-major: world x padded_pixels uchar4), the de-interleaved W x H image.
+void launch_assemble(const DTiling& tl, const uchar4* gathered, uchar4* rgba_out, const LaunchCfg& cfg);
 }  // namespace crt

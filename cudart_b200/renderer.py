@@ -36,7 +36,8 @@ class B200Renderer:
     def __init__(self, scene: FlatScene, width: int, height: int, samples: int = 10, *, device: int = -1, rank: int = 0,
                  world: int = 1, tile_rows: int = 8, seed: int = 1234, spp_per_wave: int = 0, exact_visit: bool = False,
                  profile: bool = False, stats: bool = False, reference_topology: bool = False, smem_nodes: bool | None = None,
-                 tight_bvh: bool | None = None, dynamic_pad: bool | None = None, stream: int | None = None):
+                 tight_bvh: bool | None = None, dynamic_pad: bool | None = None, stream: int | None = None,
+                 waves_in_flight: int = 0):
         self._lib = capi.lib()
         self.width, self.height, self.samples = int(width), int(height), int(samples)
         self.rank, self.world = rank, world
@@ -46,7 +47,8 @@ class B200Renderer:
             | (0 if smem_nodes is None else (capi.CRT_FLAG_SMEM_TOP_LEVELS if smem_nodes else capi.CRT_FLAG_NO_SMEM_NODES)) \
             | (0 if tight_bvh is None else (capi.CRT_FLAG_TIGHT_BVH if tight_bvh else capi.CRT_FLAG_NO_TIGHT_BVH)) \
             | (0 if dynamic_pad is None else (capi.CRT_FLAG_DYNAMIC_PAD if dynamic_pad else capi.CRT_FLAG_STATIC_PAD))
-        opt = capi.Options(C.sizeof(capi.Options), device, rank, world, tile_rows, seed, spp_per_wave, flags, stream)
+        opt = capi.Options(C.sizeof(capi.Options), device, rank, world, tile_rows, seed, spp_per_wave, flags, stream,
+                           waves_in_flight)
         h = C.c_void_p()
         capi.check(self._lib.crt_create(C.byref(desc), self.width, self.height, C.byref(opt), C.byref(h)))
         self._h = h
@@ -54,6 +56,8 @@ class B200Renderer:
 
     # ---- the reference's five-call contract -------------------------------------------------------
     def renderOneSamplePerPixel(self, p_img=None) -> None:
+        """One more sample per pixel (``renderer.h:84``).  The library queues single samples and launches them in whole
+        wavefront batches; ``getSamplesRendered`` advances by one per call all the same."""
         capi.check(self._lib.crt_render(self._h, 1))
 
     def copyImageBytes(self, p_img=None) -> None:
@@ -81,6 +85,10 @@ class B200Renderer:
     def render(self, spp: int) -> None:
         """`spp` samples per pixel in as few wavefront batches as possible (asynchronous)."""
         capi.check(self._lib.crt_render(self._h, int(spp)))
+
+    def flush(self) -> None:
+        """Launch samples still queued by ``renderOneSamplePerPixel`` (asynchronous)."""
+        capi.check(self._lib.crt_flush(self._h))
 
     def sync(self) -> None:
         capi.check(self._lib.crt_sync(self._h))
@@ -157,6 +165,25 @@ class B200Renderer:
         capi.check(self._lib.crt_resolve_gathered(self._h, d_gathered, rgba.ctypes.data if want_rgba8 else None,
                                                   f32.ctypes.data if want_f32 else None))
         return rgba, f32
+
+    def resolve_local_rgba8_device(self):
+        """(device pointer, bytes) of this rank's owned pixels as RGBA8, compact tile-major (asynchronous)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        capi.check(self._lib.crt_resolve_local_rgba8_device(self._h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def assemble_rgba8(self, d_gathered: int):
+        """De-interleave the rank-major RGBA8 buffers of all ranks into ``h_imgPtr`` (blocking)."""
+        capi.check(self._lib.crt_assemble_rgba8(self._h, d_gathered, self.h_imgPtr.ctypes.data))
+        return self.h_imgPtr
+
+    def stream_wait_ctx(self, stream: int) -> None:
+        """`stream` waits (on the device) for everything this renderer has been asked to do so far."""
+        capi.check(self._lib.crt_stream_wait_ctx(self._h, stream))
+
+    def ctx_wait_stream(self, stream: int) -> None:
+        """The renderer's stream waits (on the device) for everything enqueued on `stream` so far."""
+        capi.check(self._lib.crt_ctx_wait_stream(self._h, stream))
 
     def close(self) -> None:
         if getattr(self, "_h", None):

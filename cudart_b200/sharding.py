@@ -51,13 +51,16 @@ def as_torch(ptr: int, shape, dtype="<f4"):
 
 
 def gather_framebuffer(renderer, group=None):
-    """All-gather every rank's compact accumulator (float4 per owned pixel). Returns the rank-major device
-    tensor [world, padded_pixels, 4] that ``B200Renderer.resolve_gathered`` consumes."""
+    """All-gather every rank's compact accumulator (float4 per owned pixel) on torch's current stream. Returns the
+    rank-major device tensor [world, padded_pixels, 4] that ``B200Renderer.resolve_gathered`` consumes (float parity
+    checks; the display path is ``gather_rgba8``).  No host synchronisation: torch's stream waits for the render on the
+    device, and the renderer's stream waits for the collective before ``resolve_gathered`` reads its result."""
     import torch
     import torch.distributed as dist
 
-    renderer.sync()
     ptr, padded = renderer.accum_device_ptr()
+    cur = torch.cuda.current_stream().cuda_stream
+    renderer.stream_wait_ctx(cur)
     local = as_torch(ptr, (padded, 4))
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     out = torch.empty((world, padded, 4), dtype=torch.float32, device=local.device)
@@ -65,4 +68,31 @@ def gather_framebuffer(renderer, group=None):
         out[0].copy_(local)
     else:
         dist.all_gather_into_tensor(out.view(-1), local.view(-1), group=group)
+    renderer.ctx_wait_stream(cur)
     return out
+
+
+def gather_rgba8(renderer, dst: int = 0, group=None):
+    """The display read-out: every rank resolves ITS pixels to RGBA8 on its own GPU (4 bytes per pixel instead of the
+    accumulator's 16), the buffers are collected on rank `dst` only (NCCL send/recv under ``torch.distributed.gather``)
+    and de-interleaved there into ``renderer.h_imgPtr``.  Returns that image on `dst`, None elsewhere.  The only host
+    synchronisation is the final device -> host copy on `dst`."""
+    import torch
+    import torch.distributed as dist
+
+    ptr, nbytes = renderer.resolve_local_rgba8_device()
+    cur = torch.cuda.current_stream().cuda_stream
+    renderer.stream_wait_ctx(cur)
+    local = as_torch(ptr, (nbytes,), "|u1")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        gathered = local
+    elif rank == dst:
+        gathered = torch.empty((world, nbytes), dtype=torch.uint8, device=local.device)
+        dist.gather(local, list(gathered.unbind(0)), dst=dst, group=group)
+    else:
+        dist.gather(local, None, dst=dst, group=group)
+        return None
+    renderer.ctx_wait_stream(cur)
+    return renderer.assemble_rgba8(gathered.data_ptr())

@@ -11,7 +11,9 @@
  *
  * There is no CPU fallback: every entry point that computes fails with CRT_ERR_CUDA when no sm_100
  * device is usable.  All functions return 0 on success, a CRT_ERR_* code otherwise and never throw
- * or exit (the reference prints and exit(1)s, cuda_error_check.h:15-21; an adapter may do that on top).
+ * or exit (the reference prints and exit(1)s, cuda_error_check.h:15-21; an adapter may do that on top):
+ * C++ exceptions of the host-side builders (bad_alloc, a thread that cannot be spawned) are caught at the
+ * boundary, on worker threads too, and come back as CRT_ERR_NOMEM / CRT_ERR_INVALID.
  * A context is not re-entrant; different contexts may be driven from different threads.
  */
 #ifndef CRT_ABI_H
@@ -66,6 +68,9 @@ typedef struct crt_options {
     uint32_t spp_per_wave;    /* samples per pixel traced per wavefront batch (0 = auto)                   */
     uint32_t flags;           /* CRT_FLAG_*                                                                */
     void* stream;             /* cudaStream_t to enqueue on (NULL: a private non-blocking stream)          */
+    uint32_t waves_in_flight; /* wavefront batches in flight, 1 or 2 (0 = default 1).  With 2, consecutive
+                                 batches run on two streams (the second one private) and overlap; everything
+                                 a caller can observe stays ordered on `stream`, and the image is unchanged   */
 } crt_options;
 
 #define CRT_FLAG_EXACT_VISIT 1u  /* no distance culling: visit exactly the leaves the reference visits     */
@@ -105,13 +110,20 @@ const char* crt_last_error(void);          /* thread-local message of the last f
 int crt_create(const crt_scene_desc* scene, uint32_t width, uint32_t height, const crt_options* opt, crt_ctx** out);
 void crt_destroy(crt_ctx* ctx);
 /* Trace `spp` more samples for every pixel this context owns and add them to its accumulator
- * (== `spp` calls of Renderer::renderOneSamplePerPixel). Asynchronous; ordered on the ctx stream. */
+ * (== `spp` calls of Renderer::renderOneSamplePerPixel). Asynchronous; ordered on the ctx stream.
+ * The reference's launcher asks for ONE sample per call (terminal_launcher.cpp:12-14) while the machine wants
+ * whole wavefront batches (spp_per_wave samples per pixel): calls that add up to less than one batch are queued
+ * on the host and launched by the call that completes the batch, by crt_flush / crt_sync, or by any read-out.
+ * crt_samples_rendered advances with every call (Renderer::samplesRendered, renderer.h:91,99); sample indices,
+ * and with them the image, do not depend on how calls were grouped. */
 int crt_render(crt_ctx* ctx, uint32_t spp);
+/* Launch whatever crt_render queued (asynchronous).  crt_sync = crt_flush + wait for the ctx stream. */
+int crt_flush(crt_ctx* ctx);
 int crt_sync(crt_ctx* ctx);
 uint32_t crt_samples_rendered(const crt_ctx* ctx);           /* Renderer::getSamplesRendered */
 /* Renderer::copyImageBytes: W*H RGBA8 into host memory, row 0 = top, float3ToUchar4(sum/spp)
- * (renderer.h:149-156) then gammaCorrectPixel (renderer.cu:495-504), alpha 255.  Rows owned by other
- * ranks are left untouched when world > 1 (use crt_resolve_gathered on the gathered buffer). */
+ * (renderer.h:149-156) then gammaCorrectPixel (renderer.cu:495-504), alpha 255.  When world > 1 the rows
+ * owned by other ranks are written as zeros (use crt_resolve_gathered / crt_assemble_rgba8 for the whole image). */
 int crt_resolve_rgba8(crt_ctx* ctx, uint8_t* dst);
 /* W*H*3 floats: radiance sums divided by the samples rendered (no clamp, no gamma). */
 int crt_resolve_f32(crt_ctx* ctx, float* dst);
@@ -140,10 +152,23 @@ int crt_trace_closest_device(crt_ctx* ctx, const void* d_rays, size_t n, void* d
 /* The context's compact accumulator: float4 (r,g,b sums, unused) per owned pixel, tile-major.
  * `padded_pixels` is identical on every rank, so an all-gather of padded_pixels*16 bytes per rank
  * yields the buffer crt_resolve_gathered expects. */
-int crt_accum_device_ptr(crt_ctx* ctx, void** d_ptr, size_t* padded_pixels);
+int crt_accum_device_ptr(crt_ctx* ctx, void** d_ptr, size_t* padded_pixels);   /* launches queued samples first */
 /* d_gathered: world x padded_pixels float4 on this context's device (rank-major).
  * Writes the full image; rgba8_dst and/or f32_dst may be NULL. */
 int crt_resolve_gathered(crt_ctx* ctx, const void* d_gathered, uint8_t* rgba8_dst, float* f32_dst);
+/* Read-out in display bytes (4 B per pixel instead of 16): every rank resolves its OWN pixels to RGBA8 on its
+ * device - *d_ptr receives a context-owned buffer of *bytes = padded_pixels * 4 bytes, compact tile-major like the
+ * accumulator, pad slots zero; asynchronous on the ctx stream - the caller collects the world buffers rank-major on one
+ * rank (ncclSend / ncclRecv, torch.distributed.gather), and that rank's crt_assemble_rgba8 de-interleaves them into the
+ * W*H RGBA8 host image (blocking, like crt_resolve_rgba8).  Byte-identical to crt_resolve_gathered's RGBA8. */
+int crt_resolve_local_rgba8_device(crt_ctx* ctx, void** d_ptr, size_t* bytes);
+int crt_assemble_rgba8(crt_ctx* ctx, const void* d_gathered, uint8_t* rgba8_dst);
+/* Stream ordering for a caller that runs its collective on ANOTHER stream than the context's, without blocking the
+ * host: crt_stream_wait_ctx makes `stream` wait for everything enqueued on the ctx stream so far (queued samples are
+ * launched first); crt_ctx_wait_stream makes the ctx stream wait for everything enqueued on `stream` so far.
+ * crt_resolve_gathered / crt_assemble_rgba8 run on the ctx stream: call crt_ctx_wait_stream after the collective. */
+int crt_stream_wait_ctx(crt_ctx* ctx, void* stream);
+int crt_ctx_wait_stream(crt_ctx* ctx, void* stream);
 
 /* ---- host scene build (replaces scene.cpp:117-165 + bvh.cpp:65-323; no GPU needed) ------------- */
 /* In: Triangle[n] in OBJ order with v1/e1/e2/normals/uvs/material ids/area filled (scene.cpp:93-134)

@@ -196,7 +196,10 @@ def test_converged_image_relative_rmse_at_equal_spp(golden, B200Renderer, name):
     assert rel_rmse(got, a) < RMSE_SLACK * floor + 0.01, (rel_rmse(got, a), floor)
     med = lambda x, y: float(np.median(np.abs(x - y) / np.maximum(y, 1e-3)))
     assert med(got, a) < RMSE_SLACK * med(b, a) + 0.005, (med(got, a), med(b, a))
-    assert abs(float(got.mean()) / float(a.mean()) - 1) < 3 * abs(float(b.mean()) / float(a.mean()) - 1) + 0.01
+    # image mean: within 4 sigma of how independent oracle estimates scatter (heavy tails: one pair is a poor yardstick)
+    means = [float(a.mean()), float(b.mean())] + [float(osc.render_accum(spp, rng=orc.RNG_COUNTER, seed=500 + k)[0].mean()) / spp for k in range(6)]
+    means = [m for m in means if np.isfinite(m)]          # the soup's slivers occasionally give the reference estimator a NaN sample
+    assert abs(float(got.mean()) - float(np.mean(means))) < 4 * float(np.std(means, ddof=1)) + 0.01 * float(np.mean(means))
 
 
 @pytest.mark.parametrize("name", SCENES)
@@ -487,3 +490,166 @@ def test_command_line_shards_over_two_gpus_identically(tmp_path):
         assert p.returncode == 0, p.stderr
         images.append(_read_png_rgba(wd / "tiny.png"))
     assert np.array_equal(images[0], images[1])
+
+
+# ---- BASELINE config 4 and its little brother: the scenes where the dynamic pad, the > 10-entry stack spill and the
+# ---- oracle's deep stack matter --------------------------------------------------------------------
+def _harvest_path_rays(name, W, H, spp, seed=2026):
+    """Every ray the oracle's path loop hands to its traversal (camera, bounce, shadow), harvested in parallel row bands."""
+    import multiprocessing as mp
+    import os
+    from tools.parity_campaign import harvest_band
+    bands = [(name, W, H, spp, seed, r, min(r + 8, H)) for r in range(0, H, 8)]
+    with mp.get_context("spawn").Pool(min(os.cpu_count() or 1, 16, len(bands))) as pool:
+        return np.concatenate(pool.map(harvest_band, bands))
+
+
+@pytest.mark.parametrize("name,min_rays", [("terrain256", 1_000_000), ("terrain707", 1_000_000)])
+def test_closest_hit_bit_exact_on_the_large_terrains(B200Renderer, name, min_rays):
+    """131 074 and 999 700 triangles (BASELINE config 4): >= 1 M path-harvested rays against the oracle's 64-entry-stack
+    restatement of the reference traversal, in the four traversal modes - tight BVH with the pad baked in, tight BVH padded
+    per visit (what crt_create picks here), reference leaves with distance culling, exact visit - bit for bit."""
+    import bench
+    W, H = 320, 240
+    fs = bench.load_scene(name, W, H)
+    rays = _harvest_path_rays(name, W, H, 5)
+    assert len(rays) >= min_rays
+    want = orc.OracleScene(fs).trace_closest(rays)
+    assert (want["tri"] != MISS).mean() > 0.5
+    auto = B200Renderer(fs, W, H)
+    assert auto.tight_pad_mode() == 2                      # the choice DESIGN.md 2.4 documents for these scenes
+    assert_hits_equal(auto.trace_closest(rays), want)
+    auto.close()
+    for tight, dyn, exact in ((True, False, False), (True, True, False), (False, None, False), (False, None, True)):
+        r = B200Renderer(fs, W, H, tight_bvh=tight, dynamic_pad=dyn)
+        assert_hits_equal(r.trace_closest(rays, exact_visit=exact), want)
+        r.close()
+
+
+@pytest.mark.parametrize("name", ["terrain256", "terrain707"])
+def test_render_of_the_large_terrains_is_bitwise_mode_independent_and_replays_the_oracle(B200Renderer, name):
+    """Whole pipeline on the large terrains: the four traversal modes give identical radiance sums, and those sums are the
+    oracle's same-seed replay bit for bit."""
+    import bench
+    W, H, spp = 160, 90, 4
+    fs = bench.load_scene(name, W, H)
+    want, _ = orc.OracleScene(fs).render_accum(spp, rng=orc.RNG_COUNTER, seed=77)
+    for kw in (dict(), dict(tight_bvh=True, dynamic_pad=False), dict(tight_bvh=False), dict(exact_visit=True)):
+        r = B200Renderer(fs, W, H, spp, seed=77, **kw)
+        r.render(spp)
+        assert_radiance_bit_exact(r.accum(), want)
+        r.close()
+
+
+@pytest.mark.parametrize("name", ["cornellSphere", "monkeys"])
+def test_same_seed_replay_is_bit_exact_at_1920x1080(golden, B200Renderer, name):
+    """BASELINE configs 2 / 3 at their full frame size, 8 spp: 16.6 M paths replayed by the OpenMP oracle on the box's
+    host cores and compared with the B200 image bit for bit; the RGBA8 frame follows from the same sums."""
+    fs, _ = golden(name)
+    W, H, spp = 1920, 1080, 8
+    big = fs.with_resolution(W, H)
+    r = B200Renderer(big, W, H, spp, seed=2026)
+    r.render(spp)
+    got = r.accum()
+    r.copyImageBytes()
+    rgba = r.h_imgPtr.copy()
+    r.close()
+    want, _ = orc.OracleScene(big).render_accum(spp, rng=orc.RNG_COUNTER, seed=2026)
+    assert_radiance_bit_exact(got, want)
+    assert np.array_equal(rgba, orc.resolve_rgba8(want, spp))
+
+
+# ---- the literal Renderer seam, wave slots, display read-out ------------------------------------------------------------
+def test_literal_seam_is_batched_internally(golden, B200Renderer):
+    """TerminalLauncher::render calls renderOneSamplePerPixel once per sample (terminal_launcher.cpp:12-14).  The library
+    queues those calls and launches whole wavefront batches: the presented counter advances by one per call, kernels are
+    only launched when a batch fills (or at read-out), and the image equals render(N) bit for bit."""
+    fs, g = golden("cornellSphere")
+    W, H, N = g["W"], g["H"], 11
+    a = B200Renderer(fs, W, H, N, spp_per_wave=4)
+    for s in range(N):
+        assert a.getSamplesRendered() == s
+        a.renderOneSamplePerPixel(a.getImgBytesPointer())
+        if s == 5:
+            a.copyImageBytes()                     # a read-out in mid-stream launches what is queued; the image does not care
+    b = B200Renderer(fs, W, H, N, spp_per_wave=4)
+    for s in range(3):
+        b.renderOneSamplePerPixel()
+    assert b.getSamplesRendered() == 3
+    b.flush()
+    c3 = b.counters()
+    assert c3["samples"] == 3 * W * H and c3["kernel_launches"] == 15           # one (partial) wave: 3 + 2 * 6 launches
+    for s in range(8):
+        b.renderOneSamplePerPixel()
+    ref = B200Renderer(fs, W, H, N, spp_per_wave=4)
+    ref.render(N)
+    assert a.getSamplesRendered() == b.getSamplesRendered() == N
+    cb = b.counters()
+    assert cb["samples"] == N * W * H and cb["kernel_launches"] == 15 * 3       # 3 + 8 samples: waves of 3, 4 and 4
+    assert np.array_equal(a.accum(), ref.accum()) and np.array_equal(b.accum(), ref.accum())
+    a.copyImageBytes()
+    ref.copyImageBytes()
+    assert np.array_equal(a.h_imgPtr, ref.h_imgPtr)
+    for r in (a, b, ref):
+        r.close()
+
+
+@pytest.mark.parametrize("name", ["cornellSphere", "terrain64"])
+def test_two_waves_in_flight_are_bitwise_invisible(golden, B200Renderer, name):
+    """crt_options.waves_in_flight = 2: consecutive wavefront batches on two streams, accumulation chained in wave order."""
+    fs, g = golden(name)
+    W, H = g["W"], g["H"]
+    one = B200Renderer(fs, W, H, 7, spp_per_wave=2)
+    one.render(7)
+    two = B200Renderer(fs, W, H, 7, spp_per_wave=2, waves_in_flight=2)
+    two.render(3)
+    two.render(4)
+    assert np.array_equal(one.accum(), two.accum())
+    assert one.counters()["extend_rays"] == two.counters()["extend_rays"]
+    one.close()
+    two.close()
+
+
+def test_display_readout_in_bytes_equals_the_gathered_resolve(golden, B200Renderer):
+    """crt_resolve_local_rgba8_device on every rank + crt_assemble_rgba8 on the collector == crt_resolve_gathered's RGBA8
+    == the unsharded image (world = 3 contexts on one device stand in for three GPUs; ragged last tile)."""
+    import torch
+    from cudart_b200.sharding import as_torch
+    fs, g = golden("monkeys")
+    W, H, spp, world = g["W"], 50, 3, 3
+    fs = fs.with_resolution(W, H)
+    full = B200Renderer(fs, W, H, spp)
+    full.render(spp)
+    full.copyImageBytes()
+    parts = [B200Renderer(fs, W, H, spp, rank=k, world=world) for k in range(world)]
+    nbytes = parts[0].accum_device_ptr()[1] * 4
+    gathered = torch.zeros(world, nbytes, dtype=torch.uint8, device="cuda")
+    for k, p in enumerate(parts):
+        p.render(spp)
+        ptr, n = p.resolve_local_rgba8_device()
+        assert n == nbytes
+        p.sync()
+        gathered[k].copy_(as_torch(ptr, (n,), "|u1"))
+    torch.cuda.synchronize()
+    img = parts[1].assemble_rgba8(gathered.data_ptr())
+    assert np.array_equal(img, full.h_imgPtr)
+    for p in parts + [full]:
+        p.close()
+
+
+def test_malformed_scenes_are_rejected_not_read_out_of_bounds(golden, B200Renderer):
+    """A leaf whose offset is negative (a 32-bit wrap used to pass), texture indices below -1, an empty material table."""
+    import dataclasses
+    from cudart_b200 import capi
+    fs, g = golden("cornell")
+    nodes = fs.nodes.copy()
+    leaf = int(np.nonzero(nodes["numTriangles"] > 0)[0][0])
+    nodes["offset"][leaf] = -1
+    with pytest.raises(capi.CrtError, match="malformed"):
+        B200Renderer(dataclasses.replace(fs, nodes=nodes), 16, 16)
+    mi = fs.mat_indices.copy()
+    mi.reshape(-1, 2)[0, 1] = -2
+    with pytest.raises(capi.CrtError, match="texture index"):
+        B200Renderer(dataclasses.replace(fs, mat_indices=mi), 16, 16)
+    with pytest.raises(capi.CrtError, match="no materials"):
+        B200Renderer(dataclasses.replace(fs, mat_floats=fs.mat_floats[:0], mat_indices=fs.mat_indices[:0]), 16, 16)

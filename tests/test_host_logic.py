@@ -79,6 +79,16 @@ local[: len(rows) * W] = torch.from_numpy(img[rows].reshape(-1, 4))       # this
 out = torch.empty(world * local.shape[0], 4)
 dist.all_gather_into_tensor(out.view(-1), local.view(-1))
 ok = np.array_equal(deinterleave(out.numpy().reshape(world, -1, 4), W, H, world, tr), img)
+# the display read-out (sharding.gather_rgba8): RGBA8 resolved per rank, collected on rank 0 only, de-interleaved there
+img8 = (img * 255).astype(np.uint8)
+local8 = torch.zeros(padded_rows(H, world, tr) * W, 4, dtype=torch.uint8)
+local8[: len(rows) * W] = torch.from_numpy(img8[rows].reshape(-1, 4))
+if rank == 0:
+    got8 = torch.empty(world, local8.numel(), dtype=torch.uint8)
+    dist.gather(local8.view(-1), list(got8.unbind(0)), dst=0)
+    ok = ok and np.array_equal(deinterleave(got8.numpy().reshape(world, -1, 4), W, H, world, tr), img8)
+else:
+    dist.gather(local8.view(-1), None, dst=0)
 t = torch.tensor([1.0 if ok else 0.0]); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if t.item() == 1.0 else 1)
