@@ -66,6 +66,7 @@ SYMBOLS = {
     "crt_flush": (C.c_int, [C.c_void_p]),
     "crt_sync": (C.c_int, [C.c_void_p]),
     "crt_samples_rendered": (C.c_uint32, [C.c_void_p]),
+    "crt_spp_per_wave": (C.c_uint32, [C.c_void_p]),
     "crt_resolve_rgba8": (C.c_int, [C.c_void_p, C.c_void_p]),
     "crt_resolve_f32": (C.c_int, [C.c_void_p, C.c_void_p]),
     "crt_read_accum": (C.c_int, [C.c_void_p, C.c_void_p]),

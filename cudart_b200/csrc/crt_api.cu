@@ -140,7 +140,8 @@ struct HostSceneCache {
     std::vector<WideNode> wide;             // tight tree (if any) followed by the reference-leaf tree
     std::vector<TriIsect> isect;
     std::vector<TriShade> shade;
-    std::vector<TightRecord> tight_records;
+    std::vector<TriIsect> tight_isect;      // the tight tree's triangle records, hot part (what every test reads)
+    std::vector<float4> tight_gate;         // ... and their reference-leaf boxes (read for would-be winners only)
     std::vector<float4> light_boxes;
     WideStats wide_stats{};
     uint32_t n_tight_wide = 0, tight_split = 0, n_front = 0;
@@ -198,7 +199,7 @@ struct crt_ctx {
     HostSceneCache host_scene;
     uint64_t scene_rebuilds = 0, scene_uploads = 0, scene_upload_bytes = 0;
     // scene
-    DevBuf<float4> wide, tri_isect, tri_shade, tri_tight, mats, light_boxes;
+    DevBuf<float4> wide, tri_isect, tri_shade, tri_tight, tri_gate, mats, light_boxes;
     uint32_t tight_split = 0, tight_nodes = 0;
     DevBuf<uint32_t> lights, tex_dims, tex_offsets;
     DevBuf<float> tex_data;
@@ -237,7 +238,7 @@ int upload(DevBuf<T>& b, const void* src, size_t count, cudaStream_t s) {
 void free_all(crt_ctx* c) {
     cudaSetDevice(c->device);
     c->host_scene.unpin();
-    c->wide.release(); c->tri_isect.release(); c->tri_shade.release(); c->tri_tight.release(); c->mats.release();
+    c->wide.release(); c->tri_isect.release(); c->tri_shade.release(); c->tri_tight.release(); c->tri_gate.release(); c->mats.release();
     c->lights.release(); c->light_boxes.release(); c->tex_dims.release(); c->tex_offsets.release(); c->tex_data.release();
     for (WaveSlot& w : c->slot) w.release();
     c->stats.release(); c->accum.release();
@@ -348,8 +349,23 @@ static int derive_host_scene(crt_ctx* c, const crt_scene_desc* s, const Fingerpr
     hc.n_front = (uint32_t)(n_tight_wide ? n_tight_wide : wide.size());    // the tree the render path's rays walk
     hc.n_tight_wide = n_tight_wide;
     hc.dynamic_pad = n_tight_wide && tight.dynamic_pad;
-    hc.tight_records.swap(tight.records);
-    if (!n_tight_wide) hc.tight_records.clear();
+    hc.tight_isect.clear();
+    hc.tight_gate.clear();
+    if (n_tight_wide) {
+        // The builder's 80-byte records split by temperature: a leaf of eight 48-byte hot records spans three 128-byte
+        // lines instead of five, and the 32-byte gates are only touched by candidates that would win.
+        hc.tight_isect.resize(tight.records.size());
+        hc.tight_gate.resize(2 * tight.records.size());
+        for (size_t i = 0; i < tight.records.size(); i++) {
+            const TightRecord& r = tight.records[i];
+            TriIsect& h = hc.tight_isect[i];
+            memcpy(h.v1, r.v1, 12); h.index = r.origIdx;
+            memcpy(h.e1, r.e1, 12); h.leafFirst = r.leafFirst;
+            memcpy(h.e2, r.e2, 12); h.materialId = r.materialId;
+            hc.tight_gate[2 * i] = make_float4(r.gateLo[0], r.gateLo[1], r.gateLo[2], 0.f);
+            hc.tight_gate[2 * i + 1] = make_float4(r.gateHiX, r.gateHiY, r.gateHiZ, 0.f);
+        }
+    }
     hc.region_lo = region_lo; hc.region_hi = region_hi;
     {   // the reference leaf holding each light triangle
         hc.light_boxes.assign(2 * (size_t)s->n_lights, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -372,7 +388,7 @@ static int derive_host_scene(crt_ctx* c, const crt_scene_desc* s, const Fingerpr
         }
         hc.coords_bounded = bounded;
     }
-    hc.pin(hc.wide); hc.pin(hc.isect); hc.pin(hc.shade); hc.pin(hc.tight_records);
+    hc.pin(hc.wide); hc.pin(hc.isect); hc.pin(hc.shade); hc.pin(hc.tight_isect); hc.pin(hc.tight_gate);
     hc.fp = fp;
     hc.valid = true;
     c->scene_rebuilds++;
@@ -445,8 +461,8 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     UP(wide, hc.wide.data(), hc.wide.size() * 8);
     UP(tri_isect, hc.isect.data(), hc.isect.size() * 3);
     UP(tri_shade, hc.shade.data(), hc.shade.size() * 5);
-    if (n_tight_wide) { UP(tri_tight, hc.tight_records.data(), hc.tight_records.size() * 5); }
-    else c->tri_tight.release();
+    if (n_tight_wide) { UP(tri_tight, hc.tight_isect.data(), hc.tight_isect.size() * 3); UP(tri_gate, hc.tight_gate.data(), hc.tight_gate.size()); }
+    else { c->tri_tight.release(); c->tri_gate.release(); }
     UP(mats, mats.data(), mats.size());
     UP(lights, s->light_indices, s->n_lights);
     UP(light_boxes, hc.light_boxes.data(), hc.light_boxes.size());
@@ -474,6 +490,7 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     if (!(c->flags & CRT_FLAG_NO_SMEM_NODES) && (n_front <= kMaxSmemNodes || (c->flags & CRT_FLAG_SMEM_TOP_LEVELS)))
         sc.n_smem_nodes = std::min<uint32_t>((uint32_t)n_front, kMaxSmemNodes);
     sc.tri_tight = n_tight_wide ? c->tri_tight.p : nullptr;
+    sc.tri_gate = n_tight_wide ? c->tri_gate.p : nullptr;
     sc.dyn_pad = hc.dynamic_pad ? 1 : 0;
     sc.ref_root = n_tight_wide;
     sc.region_lo[0] = hc.region_lo.x; sc.region_lo[1] = hc.region_lo.y; sc.region_lo[2] = hc.region_lo.z;
@@ -731,6 +748,7 @@ int crt_sync(crt_ctx* c) {
 }
 
 uint32_t crt_samples_rendered(const crt_ctx* c) { return c ? c->samples : 0; }
+uint32_t crt_spp_per_wave(const crt_ctx* c) { return c ? c->spp_per_wave : 0; }
 
 static int resolve_common(crt_ctx* c, const float4* src, bool gathered, uint8_t* rgba_dst, float* f32_dst, int f32_mode) {
     int rc = crt_flush(c);

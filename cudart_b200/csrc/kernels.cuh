@@ -12,7 +12,9 @@ struct DScene {
     const float4* wide;        // n_wide x 8 float4  (WideNode)
     const float4* tri_isect;   // n_tris x 3 float4  (TriIsect)
     const float4* tri_shade;   // n_tris x 5 float4  (TriShade)
-    const float4* tri_tight;   // n_tris x 5 float4  (TightRecord, tight-BVH order); null when the tight BVH is off
+    const float4* tri_tight;   // n_tris x 3 float4  (v1|index, e1|leafFirst, e2|material in tight-BVH order); null when the tight BVH is off
+    const float4* tri_gate;    // n_tris x 2 float4  (tight-BVH order): the exact box of the triangle's reference leaf, read only
+                               // for a candidate that would become the closest hit
     const float4* mats;        // n_mats x 4 float4: (kd, bsdf) (ka, texKdIdx) (ks, 0) (ns, ni, diffuseCoefficient, 0)
     const uint32_t* lights;
     const float4* light_boxes; // per light: the reference leaf box holding it (lo.xyz, hi.xyz), for the shadow seed
@@ -77,7 +79,7 @@ struct DWave {
 
 struct LaunchCfg { int sms; cudaStream_t stream; int trav_blocks; /* traversal CTAs per SM, 0 = the compiled default */ };
 
-constexpr uint32_t kMaxSmemNodes = 288;        // 36 KB of nodes + 20 KB of stack per CTA, 4 CTAs per SM: 224 of 227 KB
+constexpr uint32_t kMaxSmemNodes = 256;        // 256 x 144 B = 36 KB of nodes + 20 KB of stack (+ 1 KB reserved) per CTA, 4 CTAs per SM: 228 KB
 int configure_kernels();                       // opt the traversal kernels into > 48 KB of dynamic shared memory
 
 void launch_raygen(const DScene& sc, const DTiling& tl, const DWave& wv, uint32_t first_sample, uint32_t wave_spp,

@@ -81,6 +81,10 @@ class B200Renderer:
     def getSamplesRendered(self) -> int:
         return int(self._lib.crt_samples_rendered(self._h))
 
+    def spp_per_wave(self) -> int:
+        """Samples per pixel the library traces in one wavefront batch."""
+        return int(self._lib.crt_spp_per_wave(self._h))
+
     # ---- batch API ------------------------------------------------------------------------------------
     def render(self, spp: int) -> None:
         """`spp` samples per pixel in as few wavefront batches as possible (asynchronous)."""

@@ -121,6 +121,7 @@ int crt_render(crt_ctx* ctx, uint32_t spp);
 int crt_flush(crt_ctx* ctx);
 int crt_sync(crt_ctx* ctx);
 uint32_t crt_samples_rendered(const crt_ctx* ctx);           /* Renderer::getSamplesRendered */
+uint32_t crt_spp_per_wave(const crt_ctx* ctx);               /* samples per pixel in one wavefront batch of this context */
 /* Renderer::copyImageBytes: W*H RGBA8 into host memory, row 0 = top, float3ToUchar4(sum/spp)
  * (renderer.h:149-156) then gammaCorrectPixel (renderer.cu:495-504), alpha 255.  When world > 1 the rows
  * owned by other ranks are written as zeros (use crt_resolve_gathered / crt_assemble_rgba8 for the whole image). */

@@ -68,7 +68,7 @@ def test_closest_hit_is_independent_of_interior_topology(golden, B200Renderer, n
 
 @pytest.mark.parametrize("smem", [False, True], ids=["global-nodes", "smem-top-levels"])
 def test_closest_hit_is_independent_of_node_staging(golden, B200Renderer, smem):
-    """Nodes fetched from L1/L2 only, or the top 288 staged in (swizzled) shared memory with the rest global (monkeys)."""
+    """Nodes fetched from L1/L2 only, or the top 256 staged in shared memory with the rest global (monkeys)."""
     for name in ("cornellSphere", "monkeys"):
         fs, g = golden(name)
         r = B200Renderer(fs, g["W"], g["H"], smem_nodes=smem)
