@@ -253,6 +253,40 @@ def ncu_per_ray(workload):
         return None
 
 
+def cli_multi_gpu_check(gpus):
+    """`./CudaRT --gpus N` (one process, one context and one host thread per GPU, ncclCommInitAll + ncclSend/ncclRecv of the
+    RGBA8 tiles to GPU 0) against `--gpus 1` on the hand-written `tiny` scene: the two PNG files must be byte-identical.
+    Runs inside the multi-GPU bench so that this in-process NCCL path is exercised on the driver's >= 2-GPU boxes."""
+    import hashlib
+    import tempfile
+    cli = os.path.join(ROOT, "cudart_b200", "CudaRT")
+    tiny = os.path.join(ROOT, "tests", "golden", "tiny")
+    if not os.path.exists(cli):
+        return {"skipped": "cudart_b200/CudaRT is not built"}
+    out = {"gpus": gpus, "scene": "tiny 70x45, 16 spp"}
+    with tempfile.TemporaryDirectory() as tmp:
+        with open(os.path.join(tmp, ".env"), "w") as f:
+            f.write("MESHES_PATH=%s/meshes\nCAMERA_PATH=%s/settings\nTEXTURES_PATH=%s/textures\n" % (tiny, tiny, tiny))
+        digests = []
+        for n in (1, gpus):
+            wd = os.path.join(tmp, "build%d" % n)
+            os.makedirs(wd)
+            env = {k: v for k, v in os.environ.items() if k not in ("CUDA_VISIBLE_DEVICES",)}
+            t0 = time.perf_counter()
+            try:
+                p = subprocess.run([cli, "-f", "tiny", "-s", "16", "-w", "70", "-h", "45", "--gpus", str(n)], cwd=wd, env=env,
+                                   capture_output=True, text=True, timeout=300)
+            except subprocess.TimeoutExpired:
+                return dict(out, error="timeout with --gpus %d" % n)
+            if p.returncode != 0:
+                return dict(out, error=(p.stderr or p.stdout)[-300:])
+            out["seconds_gpus_%d" % n] = round(time.perf_counter() - t0, 2)
+            digests.append(hashlib.sha256(open(os.path.join(wd, "tiny.png"), "rb").read()).hexdigest())
+    out["identical_png"] = digests[0] == digests[1]
+    out["sha256"] = digests[0][:16]
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 def run_reference(args, scene, W, H, total_spp):
     rank = int(os.environ.get("RANK", "0"))
@@ -588,6 +622,8 @@ def main():
         }
         if world == 1 and not args.no_configs and args.workload == "cornellSphere_1080p":
             line["cuda_reference"] = reference_cuda_run(scene, W, H, 64, h.uuid or h.local)
+        if world > 1 and not args.no_configs:
+            line["cli_multi_gpu"] = cli_multi_gpu_check(world)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(scene, W, H)
             if m.get("time_to_full_spp_s"):

@@ -8,8 +8,8 @@
 // working directory (`-o` is advertised by the reference's usage text but never parsed, D24 - same here).
 // The B200Renderer below is the third implementation of the reference's Renderer seam (renderer.h:78-100):
 // TerminalLauncher::render's call sequence (terminal_launcher.cpp:10-16) drives it unchanged.
-// `--cpu` has no implementation in this repository: it hands over to the unmodified reference binary
-// (oracle/_ref/CudaRT_ref, a reported baseline) when that is present and fails loudly otherwise.
+// `--cpu` has no implementation in this repository: it hands over to an unmodified reference binary ($CUDART_REFERENCE,
+// else baseline/_ref/CudaRT_ref next to this package) when one is installed and fails loudly otherwise.
 #include <cuda_runtime.h>
 #include <nccl.h>
 #include <unistd.h>
@@ -42,7 +42,9 @@ namespace {
 #define NCCL(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) fatal(string(#call) + ": " + ncclGetErrorString(r_)); } while (0)
 
 // The reference's Renderer contract (renderer.h:78-100) on top of the C ABI; one context per GPU, the image
-// sharded as interleaved row tiles, ONE NCCL all-gather of the compact accumulators when the image is read.
+// sharded as interleaved row tiles.  Read-out is the path's ONE exchange: every GPU resolves its own tiles to RGBA8
+// (4 bytes per pixel instead of the accumulator's 16) and sends them to GPU 0 over NVLink (ncclSend / ncclRecv in one
+// group, on the render streams, no host synchronisation in between); GPU 0 de-interleaves and copies to the host.
 class B200Renderer {
 public:
     bool useCuda = true;
@@ -72,19 +74,13 @@ public:
             vector<int> devs(gpus);
             for (int g = 0; g < gpus; g++) devs[g] = g;
             NCCL(ncclCommInitAll(comms.data(), gpus, devs.data()));
-            size_t padded = 0;
             void* p = nullptr;
-            CRT(crt_accum_device_ptr(ctx[0], &p, &padded));
-            gathered.resize(gpus);
-            for (int g = 0; g < gpus; g++) {
-                CUDA(cudaSetDevice(g));
-                CUDA(cudaMalloc(&gathered[g], padded * 16 * (size_t)gpus));
-            }
-            // NCCL builds its channels lazily on the first collective (hundreds of ms): do that here, with the other
+            CRT(crt_resolve_local_rgba8_device(ctx[0], &p, &tile_bytes));
+            CUDA(cudaSetDevice(0));
+            CUDA(cudaMalloc(&gathered, tile_bytes * (size_t)gpus));
+            // NCCL builds its channels lazily on the first exchange (hundreds of ms): do that here, with the other
             // one-time setup, so that the timed render (main.cpp:173-176 times Launcher::render only) does not pay for it
-            NCCL(ncclGroupStart());
-            for (int g = 0; g < gpus; g++) NCCL(ncclAllGather(gathered[g], gathered[g], 4, ncclFloat, comms[g], streams[g]));
-            NCCL(ncclGroupEnd());
+            exchange();
             for (int g = 0; g < gpus; g++) { CUDA(cudaSetDevice(g)); CUDA(cudaStreamSynchronize(streams[g])); }
         }
         h_img.assign((size_t)w * h * 4, 0);
@@ -92,7 +88,7 @@ public:
     ~B200Renderer() {
         for (size_t g = 0; g < ctx.size(); g++) {
             cudaSetDevice((int)g);
-            if (g < gathered.size() && gathered[g]) cudaFree(gathered[g]);
+            if (g == 0 && gathered) cudaFree(gathered);
             crt_destroy(ctx[g]);
             if (g < comms.size()) ncclCommDestroy(comms[g]);
             cudaStreamDestroy(streams[g]);
@@ -105,8 +101,8 @@ public:
         vector<thread> workers;
         vector<string> errors(ctx.size());
         for (size_t g = 0; g < ctx.size(); g++)
-            workers.emplace_back([&, g] {
-                if (crt_render(ctx[g], spp) != CRT_OK || crt_sync(ctx[g]) != CRT_OK) errors[g] = crt_last_error();
+            workers.emplace_back([&, g] {             // enqueue only: nothing waits for the device until the image is read
+                if (crt_render(ctx[g], spp) != CRT_OK || crt_flush(ctx[g]) != CRT_OK) errors[g] = crt_last_error();
             });
         for (thread& t : workers) t.join();
         for (const string& e : errors) if (!e.empty()) fatal("crt_render: " + e);
@@ -114,16 +110,26 @@ public:
     }
     void copyImageBytes(uint8_t*) {                      // Renderer::copyImageBytes: gather, resolve, gamma
         if (ctx.size() == 1) { CRT(crt_resolve_rgba8(ctx[0], h_img.data())); return; }
-        size_t padded = 0;
-        NCCL(ncclGroupStart());
+        exchange();
+        CRT(crt_assemble_rgba8(ctx[0], gathered, h_img.data()));        // the one blocking call: de-interleave + D2H on GPU 0
+        for (size_t g = 1; g < ctx.size(); g++) CRT(crt_sync(ctx[g]));
+    }
+    // every GPU: resolve its own tiles to RGBA8 on its render stream; GPUs 1..N-1 send them to GPU 0 (all enqueued, no host waits)
+    void exchange() {
+        vector<void*> local(ctx.size());
         for (size_t g = 0; g < ctx.size(); g++) {
-            void* p = nullptr;
-            CRT(crt_accum_device_ptr(ctx[g], &p, &padded));
-            NCCL(ncclAllGather(p, gathered[g], padded * 4, ncclFloat, comms[g], streams[g]));
+            size_t bytes = 0;
+            CRT(crt_resolve_local_rgba8_device(ctx[g], &local[g], &bytes));
+            if (bytes != tile_bytes) fatal("copyImageBytes: ranks disagree about the tile buffer size");
+        }
+        CUDA(cudaSetDevice(0));
+        CUDA(cudaMemcpyAsync(gathered, local[0], tile_bytes, cudaMemcpyDeviceToDevice, streams[0]));
+        NCCL(ncclGroupStart());
+        for (size_t g = 1; g < ctx.size(); g++) {
+            NCCL(ncclRecv((char*)gathered + g * tile_bytes, tile_bytes, ncclUint8, (int)g, comms[0], streams[0]));
+            NCCL(ncclSend(local[g], tile_bytes, ncclUint8, 0, comms[g], streams[g]));
         }
         NCCL(ncclGroupEnd());
-        CRT(crt_resolve_gathered(ctx[0], gathered[0], h_img.data(), nullptr));
-        for (size_t g = 1; g < ctx.size(); g++) CRT(crt_sync(ctx[g]));
     }
     uint8_t* getImgBytesPointer() { return h_img.data(); }
     void createMaterialsData() {}
@@ -148,12 +154,13 @@ private:
     vector<crt_ctx*> ctx;
     vector<cudaStream_t> streams;
     vector<ncclComm_t> comms;
-    vector<void*> gathered;
+    void* gathered = nullptr;                           // GPU 0: N x tile_bytes of RGBA8, rank-major
+    size_t tile_bytes = 0;
 };
 
 // TerminalLauncher::render (terminal_launcher.cpp:10-16), batched: the renderer is told how many samples follow
 // so that it can trace them in large wavefront batches instead of one launch sequence per sample.
-void launch(B200Renderer& r, unsigned progress_every, const string& outFile) {
+void launch(B200Renderer& r, unsigned progress_every, const string& outFile, unsigned stop_after_writes) {
     uint8_t* img = r.getImgBytesPointer();
     if (progress_every == 0) {
         r.render((unsigned)r.getSamples());
@@ -168,6 +175,10 @@ void launch(B200Renderer& r, unsigned progress_every, const string& outFile) {
                 r.copyImageBytes(img);
                 write_png_rgba8(outFile, r.h_img.data(), r.getWidth(), r.getHeight());
                 cout << "\r" << done << " / " << total << " samples per pixel" << flush;
+                if (stop_after_writes && --stop_after_writes == 0) {     // tests: what an interrupted run leaves behind
+                    cout << endl;
+                    exit(0);
+                }
             }
         }
         cout << endl;
@@ -187,7 +198,7 @@ string self_dir() {
 }  // namespace
 
 int main(int argc, char* argv[]) {
-    int samples = 10, width = 640, height = 480, gpus = 1, progress = 0;
+    int samples = 10, width = 640, height = 480, gpus = 1, progress = 0, stopAfterProgress = 0;
     string outFile = "out.png", sceneName = "cornell";
     string objDir, cameraDir, texturePath, dumpScene, metricsFile;
     const string envPath = "../.env";
@@ -229,6 +240,7 @@ int main(int argc, char* argv[]) {
     value_of("-h", "-h", height);
     value_of("--gpus", "--gpus", gpus);
     value_of("--progress", "--progress", progress);
+    value_of("--stop-after-progress", "--stop-after-progress", stopAfterProgress);
     if (find(args.begin(), args.end(), "--cpu") < args.end()) executeOnCpu = true;
     if (find(args.begin(), args.end(), "--no-render") < args.end()) noRender = true;
     auto str_of = [&](const char* flag, string& dst) {
@@ -246,8 +258,9 @@ int main(int argc, char* argv[]) {
 
     if (executeOnCpu) {
         // The CPU path is the reference's own; this repository ships no CPU renderer and no fallback.
-        const string ref = self_dir() + "/../oracle/_ref/CudaRT_ref";
-        if (access(ref.c_str(), X_OK) != 0) fatal("--cpu: the reference binary " + ref + " is not built here (make -C oracle ref); the B200 path has no CPU fallback");
+        const char* env_ref = getenv("CUDART_REFERENCE");
+        const string ref = env_ref ? string(env_ref) : self_dir() + "/../baseline/_ref/CudaRT_ref";
+        if (access(ref.c_str(), X_OK) != 0) fatal("--cpu: no reference binary at " + ref + " (set CUDART_REFERENCE to an unmodified CudaRT build); the B200 path has no CPU renderer and no fallback");
         execv(ref.c_str(), argv);
         fatal("--cpu: cannot exec " + ref);
     }
@@ -284,7 +297,7 @@ int main(int argc, char* argv[]) {
 
     B200Renderer renderer(scene, (unsigned)width, (unsigned)height, (unsigned)samples, gpus);
     auto start = high_resolution_clock::now();
-    launch(renderer, (unsigned)max(progress, 0), outFile);
+    launch(renderer, (unsigned)max(progress, 0), outFile, (unsigned)max(stopAfterProgress, 0));
     auto stop = high_resolution_clock::now();
     write_png_rgba8(outFile, renderer.h_img.data(), (unsigned)width, (unsigned)height);     // Launcher::saveToImage
 
