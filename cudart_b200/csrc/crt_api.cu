@@ -163,17 +163,17 @@ struct HostSceneCache {
 // waves run on two streams so that the latency-bound shade launches of one wave can fill the issue slots and launch
 // tails the traversal of the other leaves idle.
 struct WaveSlot {
-    DevBuf<float4> rq_o[2], rq_d[2], hits, sq_o, sq_d, sq_c, st_mask, color;
+    DevBuf<float4> rq_o[2], rq_d[2], rq_m[2], hits, sq_o, sq_d, sq_c, color;
     DevBuf<uint32_t> rq_path[2], sq_path;
-    DevBuf<uint2> st_key;
+    DevBuf<uint2> rq_k[2];
     DevBuf<DCounters> counters;
     DWave wv{};
     LaunchCfg cfg{};
     cudaEvent_t accumulated = nullptr;       // recorded after this slot's k_accumulate: the next wave's accumulate waits for it
     void release() {
-        for (int i = 0; i < 2; i++) { rq_o[i].release(); rq_d[i].release(); rq_path[i].release(); }
-        hits.release(); sq_o.release(); sq_d.release(); sq_c.release(); st_mask.release(); color.release();
-        sq_path.release(); st_key.release(); counters.release();
+        for (int i = 0; i < 2; i++) { rq_o[i].release(); rq_d[i].release(); rq_path[i].release(); rq_m[i].release(); rq_k[i].release(); }
+        hits.release(); sq_o.release(); sq_d.release(); sq_c.release(); color.release();
+        sq_path.release(); counters.release();
         if (accumulated) cudaEventDestroy(accumulated);
         accumulated = nullptr;
     }
@@ -525,8 +525,11 @@ static int create_impl(const crt_scene_desc* s, uint32_t W, uint32_t H, const cr
     if (o.tile_rows == 0) o.tile_rows = 8;
     if (o.seed == 0) o.seed = 1234;
     if (const char* e = getenv("CRT_WAVES_IN_FLIGHT")) { if (!o.waves_in_flight) o.waves_in_flight = (uint32_t)atoi(e); }   // A/B measurements
-    if (o.waves_in_flight == 0) o.waves_in_flight = 1;
-    if (o.waves_in_flight > 2) return fail(CRT_ERR_INVALID, "crt_create: waves_in_flight %u (1 or 2)", o.waves_in_flight);
+    if (o.waves_in_flight > 2) return fail(CRT_ERR_INVALID, "crt_create: waves_in_flight %u (0, 1 or 2)", o.waves_in_flight);
+    // default: two batches in flight (measured +1.5 ... +3 %, profiles/r02e_waves_in_flight_ab.jsonl).  Per-stage event
+    // timing only means something when the stages do not overlap: CRT_FLAG_PROFILE runs one batch at a time.
+    if (o.waves_in_flight == 0) o.waves_in_flight = 2;
+    if (o.flags & CRT_FLAG_PROFILE) o.waves_in_flight = 1;
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -591,14 +594,17 @@ static int create_impl(const crt_scene_desc* s, uint32_t W, uint32_t H, const cr
     AL(c->accum, tl.padded_pixels);
     for (uint32_t si = 0; si < c->n_slots; si++) {
         WaveSlot& w = c->slot[si];
-        for (int i = 0; i < 2; i++) { AL(w.rq_o[i], cap); AL(w.rq_d[i], cap); AL(w.rq_path[i], cap); }
+        for (int i = 0; i < 2; i++) { AL(w.rq_o[i], cap); AL(w.rq_d[i], cap); AL(w.rq_path[i], cap); AL(w.rq_m[i], cap); AL(w.rq_k[i], cap); }
         AL(w.hits, cap); AL(w.sq_o, cap); AL(w.sq_d, cap); AL(w.sq_c, cap); AL(w.sq_path, cap);
-        AL(w.st_mask, cap); AL(w.st_key, cap); AL(w.color, cap);
+        AL(w.color, cap);
         AL(w.counters, 1);
         DWave& wv = w.wv;
-        for (int i = 0; i < 2; i++) { wv.rq_o[i] = w.rq_o[i].p; wv.rq_d[i] = w.rq_d[i].p; wv.rq_path[i] = w.rq_path[i].p; }
+        for (int i = 0; i < 2; i++) {
+            wv.rq_o[i] = w.rq_o[i].p; wv.rq_d[i] = w.rq_d[i].p; wv.rq_path[i] = w.rq_path[i].p;
+            wv.rq_m[i] = w.rq_m[i].p; wv.rq_k[i] = w.rq_k[i].p;
+        }
         wv.hits = w.hits.p; wv.sq_o = w.sq_o.p; wv.sq_d = w.sq_d.p; wv.sq_c = w.sq_c.p; wv.sq_path = w.sq_path.p;
-        wv.st_mask = w.st_mask.p; wv.st_key = w.st_key.p; wv.color = w.color.p;
+        wv.color = w.color.p;
         wv.counters = w.counters.p; wv.stats = c->stats.p; wv.capacity = (uint32_t)cap;
         w.cfg = c->cfg;
         w.cfg.stream = si == 0 ? c->stream : c->aux_stream;
@@ -640,7 +646,7 @@ static int launch_pending(crt_ctx* c) {
     const uint32_t spp = c->samples - c->launched;
     if (spp == 0 || c->tl.local_pixels == 0) { c->launched = c->samples; return CRT_OK; }
     const bool exact = c->flags & CRT_FLAG_EXACT_VISIT, stats = c->flags & CRT_FLAG_STATS;
-    const bool prof = (c->flags & CRT_FLAG_PROFILE) && c->n_slots == 1;
+    const bool prof = c->flags & CRT_FLAG_PROFILE;
     cudaEvent_t a = c->take_event(), b = c->take_event();
     CU(cudaEventRecord(a, c->stream));
     struct Span { int stage; cudaEvent_t e; };
@@ -719,7 +725,7 @@ int crt_render(crt_ctx* c, uint32_t spp) {
         // launched by the call that completes the batch (or by crt_flush / crt_sync / any read-out).  The presented counter
         // (crt_samples_rendered) advances with every call; sample indices, and therefore the image, do not depend on how
         // the samples were grouped into waves.
-        if (c->samples - c->launched < c->spp_per_wave) return (int)CRT_OK;
+        if (c->samples - c->launched < c->spp_per_wave * c->n_slots) return (int)CRT_OK;
         return launch_pending(c);
     });
 }

@@ -64,13 +64,13 @@ struct DWave {
     float4* rq_o[2];           // extend queue (ping-pong): origin.xyz, tMin
     float4* rq_d[2];           //                           dir.xyz,    tMax
     uint32_t* rq_path[2];      //                           path id
+    float4* rq_m[2];           //                           throughput.rgb, meta bits (dim | bounce<<8 | prevBsdf<<12)
+    uint2* rq_k[2];            //                           RNG key (include/crt_rng.h)
     float4* hits;              // t, u, v, tri (bits) per extend-queue slot
     float4* sq_o;              // shadow queue: origin.xyz, tMin
     float4* sq_d;              //               dir.xyz, tMax
     float4* sq_c;              //               throughput.rgb after the diffuse bounce, light ordinal (bits)
     uint32_t* sq_path;
-    float4* st_mask;           // per path: throughput.rgb, meta bits (dim | bounce<<8 | prevBsdf<<12)
-    uint2* st_key;             // per path: RNG key (include/crt_rng.h)
     float4* color;             // per path: radiance accumulated so far
     DCounters* counters;
     DStats* stats;

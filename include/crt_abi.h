@@ -68,13 +68,14 @@ typedef struct crt_options {
     uint32_t spp_per_wave;    /* samples per pixel traced per wavefront batch (0 = auto)                   */
     uint32_t flags;           /* CRT_FLAG_*                                                                */
     void* stream;             /* cudaStream_t to enqueue on (NULL: a private non-blocking stream)          */
-    uint32_t waves_in_flight; /* wavefront batches in flight, 1 or 2 (0 = default 1).  With 2, consecutive
-                                 batches run on two streams (the second one private) and overlap; everything
-                                 a caller can observe stays ordered on `stream`, and the image is unchanged   */
+    uint32_t waves_in_flight; /* wavefront batches in flight, 1 or 2 (0 = default: 2, or 1 with CRT_FLAG_PROFILE).
+                                 With 2, consecutive batches run on two streams (the second one private) and
+                                 overlap; everything a caller can observe stays ordered on `stream`, and the
+                                 image is unchanged                                                           */
 } crt_options;
 
 #define CRT_FLAG_EXACT_VISIT 1u  /* no distance culling: visit exactly the leaves the reference visits     */
-#define CRT_FLAG_PROFILE 2u      /* time every stage with CUDA events (crt_get_counters.stage_ms)          */
+#define CRT_FLAG_PROFILE 2u      /* time every stage with CUDA events (crt_get_counters.stage_ms); one batch in flight */
 #define CRT_FLAG_REFERENCE_TOPOLOGY 8u /* keep the reference's interior BVH structure (no SAH re-clustering of its leaves) */
 #define CRT_FLAG_NO_SMEM_NODES 16u /* never stage BVH nodes in shared memory (default: staged when the whole wide tree fits) */
 #define CRT_FLAG_SMEM_TOP_LEVELS 32u /* stage the top levels even when the tree does not fit entirely (A/B measurements) */
@@ -112,8 +113,9 @@ void crt_destroy(crt_ctx* ctx);
 /* Trace `spp` more samples for every pixel this context owns and add them to its accumulator
  * (== `spp` calls of Renderer::renderOneSamplePerPixel). Asynchronous; ordered on the ctx stream.
  * The reference's launcher asks for ONE sample per call (terminal_launcher.cpp:12-14) while the machine wants
- * whole wavefront batches (spp_per_wave samples per pixel): calls that add up to less than one batch are queued
- * on the host and launched by the call that completes the batch, by crt_flush / crt_sync, or by any read-out.
+ * whole wavefront batches (spp_per_wave samples per pixel, waves_in_flight of them at a time): calls that add up to
+ * less than that are queued on the host and launched by the call that completes it, by crt_flush / crt_sync, or by
+ * any read-out.
  * crt_samples_rendered advances with every call (Renderer::samplesRendered, renderer.h:91,99); sample indices,
  * and with them the image, do not depend on how calls were grouped. */
 int crt_render(crt_ctx* ctx, uint32_t spp);
