@@ -577,12 +577,13 @@ static int create_impl(const crt_scene_desc* s, uint32_t W, uint32_t H, const cr
 
     // ---- wave buffers ----
     uint32_t k = o.spp_per_wave;
-    if (k == 0) {       // auto: about 16M paths in flight in total (~3 GB of wave state; measured +12 % over 4M), within
-                        // a quarter of the free device memory, at least 1 spp per wave
+    if (k == 0) {       // auto: about 16M paths per batch (3.4 GB of wave state each; measured +12 % over 4M in round 1, and
+                        // +2 % for two batches of 16M over two of 8M: profiles/r02o_wave_size.jsonl), all batches together
+                        // within a quarter of the free device memory, at least 1 spp per batch
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        const uint64_t by_mem = std::max<uint64_t>(1u << 20, free_b / 4 / 192);
-        const uint64_t target = std::min<uint64_t>(16ull << 20, by_mem) / c->n_slots;
+        const uint64_t by_mem = std::max<uint64_t>(1u << 20, free_b / 4 / 208 / c->n_slots);
+        const uint64_t target = std::min<uint64_t>(16ull << 20, by_mem);
         k = (uint32_t)std::max<uint64_t>(1, target / std::max<uint32_t>(tl.local_pixels, 1));
         k = std::min<uint32_t>(k, 64);
     }

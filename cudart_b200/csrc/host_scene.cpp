@@ -525,6 +525,11 @@ struct TightBuilder {
     std::vector<RefNode> pool;
     std::vector<int32_t> first_child;
     std::atomic<uint32_t> next_node{0};
+    // Largest leaf, in triangles.  8 where a triangle test is cheap next to a node visit (static pad); 4 in the
+    // dynamic-pad trees, whose leaves are far less uniform in size (the warp pass lasts as long as its longest leaf):
+    // measured monkeys 1189 -> 1226, 1M terrain 602 -> 606 Msamples/s, but cornellSphere (static) 2266 -> 2048
+    // (profiles/r02n_tuning_sweep.jsonl).
+    uint32_t max_leaf = 8;
 
     void run() {
         uint32_t total = 0;
@@ -581,8 +586,15 @@ struct TightBuilder {
         // SAH with the traversal cost measured on B200: one wide-node visit costs about as much as eight triangle
         // tests (profiles/r01s_*: a wide node covers ~3 binary nodes, hence 3 per binary node), so leaves of up to 8
         // triangles beat the reference's <= 3: cornellSphere 1649 -> 1950 Msamples/s, monkeys 775 -> 815, terrain 1M 324 -> 354.
-        constexpr double kTrav = kTightTraversalCost;
-        constexpr uint32_t kMaxLeaf = 8;
+#ifndef CRT_TIGHT_TRAV
+#define CRT_TIGHT_TRAV kTightTraversalCost
+#endif
+        constexpr double kTrav = CRT_TIGHT_TRAV;          // tuning builds override it (profiles/r02n_*)
+#ifdef CRT_TIGHT_MAXLEAF
+        const uint32_t kMaxLeaf = CRT_TIGHT_MAXLEAF;
+#else
+        const uint32_t kMaxLeaf = max_leaf;
+#endif
         const bool leaf_ok = weight <= 32767u;
         if (n == 1 || (leaf_ok && weight <= 2)) return make_leaf();
         constexpr int kBins = 16;
@@ -769,6 +781,7 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
         }
         out.dynamic_pad = pad_mode == kPadDynamic;
         if (out.dynamic_pad) { infl_mn.swap(tight_mn); infl_mx.swap(tight_mx); }
+        tb.max_leaf = ub.max_leaf = out.dynamic_pad ? 4 : 8;
     }
     std::vector<uint32_t> bounded, unbounded, one(1);
     std::vector<F3> bmn, bmx;
