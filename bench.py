@@ -407,8 +407,14 @@ def measure_workload(h, workload, steps, warmup, spp_step, full=True):
 
     # ---- value: scene resident, no profiling flag, device-only step ----
     r = h.renderer(fs, W, H, total_spp)
-    for _ in range(warmup):
+    # warm-up: at least `warmup` steps AND at least 0.3 s of work (a 256x256 step lasts 2 ms: three of them would leave
+    # the clocks of a cold GPU still ramping)
+    t_w, n_w = time.perf_counter(), 0
+    while n_w < warmup or (h.world == 1 and time.perf_counter() - t_w < 0.3 and n_w < 400):   # N > 1: same count on every rank
         h.device_step(r, spp_step)
+        n_w += 1
+        if n_w % 8 == 0:
+            h.torch.cuda.synchronize()
     h.barrier()
     c0 = r.counters()
     ms, clocks = h.timed(lambda: h.device_step(r, spp_step), steps, clocks=True)
@@ -534,6 +540,11 @@ def main():
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                                    "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
 
+    # stdout carries exactly ONE line, the JSON: everything else that writes to file descriptor 1 (NCCL's version banner,
+    # library chatter) is sent to stderr from here on
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     h = Harness(args)
     world, rank = h.world, h.rank
     warmup = max(args.warmup, 3)
@@ -628,7 +639,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(scene, W, H)
             if m.get("time_to_full_spp_s"):
                 line["time_to_full_spp_s"]["cpu_reference_seconds_extrapolated"] = round(W * H * total_spp / (line["cpu_baseline"]["value"] * 1e6), 1)
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         h.dist.barrier()
         h.dist.destroy_process_group()
