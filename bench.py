@@ -624,6 +624,7 @@ def main():
             "e2e": m["e2e"],
             "seam_literal": m["seam_literal"],
             "time_to_full_spp_s": m.get("time_to_full_spp_s"),
+            "time_to_512spp_s": (m.get("time_to_full_spp_s") or {}).get("seconds") if total_spp == 512 else None,
             "gpu_launches": m["gpu_launches"],
             "stage_ms": m["stage_ms"],
             "tight_bvh": dict(m["tight_bvh"], per_ray=m.get("per_ray")),

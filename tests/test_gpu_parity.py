@@ -541,10 +541,11 @@ def test_render_of_the_large_terrains_is_bitwise_mode_independent_and_replays_th
         r.close()
 
 
-@pytest.mark.parametrize("name", ["cornellSphere", "monkeys"])
+@pytest.mark.parametrize("name", ["cornell", "cornellSphere", "monkeys"])
 def test_same_seed_replay_is_bit_exact_at_1920x1080(golden, B200Renderer, name):
-    """BASELINE configs 2 / 3 at their full frame size, 8 spp: 16.6 M paths replayed by the OpenMP oracle on the box's
-    host cores and compared with the B200 image bit for bit; the RGBA8 frame follows from the same sums."""
+    """The three bundled scenes (BASELINE configs 2 / 3 and the config-1/5 scene) at the full 1920x1080 frame, 8 spp:
+    16.6 M paths replayed by the OpenMP oracle on the box's host cores and compared with the B200 image bit for bit; the
+    RGBA8 frame follows from the same sums."""
     fs, _ = golden(name)
     W, H, spp = 1920, 1080, 8
     big = fs.with_resolution(W, H)
