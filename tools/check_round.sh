@@ -2,7 +2,7 @@
 # parity of the closest-hit modes + bench lines + per-ray instruction counts of the current build
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-O=gpurun_out/${1:-r02f}
+O=gpurun_out/${1:-check}
 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "closest_hit or bitwise or replay_is_bit_exact" 2>&1 | tail -4
 : > $O.jsonl
 for wl in cornellSphere_1080p monkeys_1080p terrain1m_1080p; do
