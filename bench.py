@@ -253,6 +253,16 @@ def ncu_per_ray(workload):
         return None
 
 
+def workload_config(workload):
+    """`config` of the JSON line: names the workload and nothing else, so that the two arms (`--impl b200` / `reference`)
+    of one workload carry the IDENTICAL dict; how a run was carried out (samples per step, batch size, sharding, the CPU
+    arm's bounded sample) is in `run`."""
+    scene, W, H, total_spp = WORKLOADS[workload]
+    return {"workload": workload, "scene": scene, "width": W, "height": H, "spp_total_config": total_spp,
+            "l2": "the wavefront state of one batch (~3.4 GB at 16.6 M paths) exceeds the %d MB L2 many times over: no explicit "
+                  "flush between timed iterations" % (L2_BYTES >> 20)}
+
+
 def cli_multi_gpu_check(gpus):
     """`./CudaRT --gpus N` (one process, one context and one host thread per GPU, ncclCommInitAll + ncclSend/ncclRecv of the
     RGBA8 tiles to GPU 0) against `--gpus 1` on the hand-written `tiny` scene: the two PNG files must be byte-identical.
@@ -309,8 +319,8 @@ def run_reference(args, scene, W, H, total_spp):
     line = {"impl": "reference", "metric": "path-tracing throughput", "value": round(value, 5), "unit": "Msamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t / args.steps, 3),
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "scene": scene, "width": W, "height": H, "spp": total_spp,
-                       "timed_sample": "%dx%d x %d spp per step" % (w, h, spp)},
+            "config": workload_config(args.workload),
+            "run": {"timed_sample": "%dx%d x %d spp per step, scaled linearly to the workload's frame" % (w, h, spp), "threads": threads},
             "cpu_baseline": {"value": round(value, 5), "unit": "Msamples/s", "cores": threads, "kind": kind,
                              "sample": "%s %dx%d %d spp per step, render time as printed by the reference binary" % (scene, w, h, spp)},
             "e2e": {"value": round(value, 5), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -615,11 +625,9 @@ def main():
             "steps": steps, "warmup": warmup, "ms_per_step": round(m["ms_per_step"], 3),
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "mrays_per_s": round(m["mrays_per_s"], 3), "rays_per_sample": round(m["rays_per_sample"], 4),
-            "config": {"workload": args.workload, "scene": scene, "width": W, "height": H, "spp_total_config": total_spp,
-                       "spp_per_step": spp_step, "spp_per_wave": m["spp_per_wave"], "parallelism": "row-tiles x%d" % world,
-                       "rng": "counter (seed 1234)",
-                       "l2": "wavefront state per wave (~%d MB) exceeds L2 (%d MB); no explicit flush" %
-                             (176 * min((16 << 20), W * H * spp_step // world) >> 20, L2_BYTES >> 20)},
+            "config": workload_config(args.workload),
+            "run": {"spp_per_step": spp_step, "spp_per_wave": m["spp_per_wave"], "parallelism": "row-tiles x%d" % world,
+                    "rng": "counter (seed 1234)"},
             "clocks": m["clocks"],
             "e2e": m["e2e"],
             "seam_literal": m["seam_literal"],
