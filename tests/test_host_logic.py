@@ -131,3 +131,41 @@ def test_scene_fingerprint_sees_every_byte():
         assert len(seen) >= 2
         assert fp(a[:-1]) != base if nbytes > 1 else True           # the length is part of it
     assert fp(np.zeros(64, np.uint8)) != fp(np.zeros(65, np.uint8))
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """include/crt_abi.h is the boundary a C (not C++) program binds: compile a C99 translation unit against it with
+    gcc -std=c99 -pedantic, link libcrt_b200.so, call it.  Without a GPU every computing entry point must come back
+    with an error code and a message - never a crash, never a CPU fallback."""
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "crt_abi.h"
+int main(void) {
+    crt_scene_desc s;
+    crt_options o;
+    crt_ctx* ctx = NULL;
+    uint64_t fp[2];
+    memset(&s, 0, sizeof s);
+    memset(&o, 0, sizeof o);
+    o.struct_size = sizeof o;
+    if (crt_abi_version() != CRT_ABI_VERSION) return 1;
+    if (crt_create(NULL, 16, 16, &o, &ctx) != CRT_ERR_INVALID) return 2;          /* null scene */
+    if (crt_create(&s, 16, 16, &o, &ctx) != CRT_ERR_INVALID || ctx != NULL) return 3; /* empty scene */
+    if (strlen(crt_last_error()) == 0) return 4;
+    if (crt_render(NULL, 1) != CRT_ERR_INVALID || crt_flush(NULL) != CRT_ERR_INVALID || crt_sync(NULL) != CRT_ERR_INVALID) return 5;
+    if (crt_samples_rendered(NULL) != 0 || crt_spp_per_wave(NULL) != 0) return 6;
+    if (crt_fingerprint("abc", 3, fp) != CRT_OK || (fp[0] == 0 && fp[1] == 0)) return 7;
+    crt_destroy(NULL);
+    printf("abi %d ok: %s\n", crt_abi_version(), crt_last_error());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "cudart_b200")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lcrt_b200", "-Wl,-rpath," + libdir], check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0, (p.returncode, p.stdout, p.stderr)
+    assert "abi 1 ok" in p.stdout
