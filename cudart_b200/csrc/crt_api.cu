@@ -183,8 +183,15 @@ struct crt_ctx {
     int device = 0;
     bool own_stream = false;
     cudaStream_t stream = nullptr;           // the context's stream: everything a caller can observe is ordered on it
-    cudaStream_t aux_stream = nullptr;       // second wave in flight (forked from / joined into `stream` inside crt_render)
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_order = nullptr;
+    // Wavefront batches run on the context's own work streams, one per wave slot.  A batch only has to follow the last
+    // operation of this context that touched what it reads or writes (scene upload, reset, a read-out of the accumulator):
+    // that point is `ev_epoch`, re-recorded on `stream` after every such operation.  `stream` itself only WAITS for a
+    // call's batches (their last launch, the accumulation), so everything a caller can observe is still ordered on it -
+    // but consecutive calls, and the consecutive batches inside one, overlap on the two work streams.
+    cudaStream_t work[2] = {nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_epoch = nullptr, ev_order = nullptr;
+    uint64_t epoch = 0, waited_epoch[2] = {~0ull, ~0ull};
+    cudaEvent_t last_accum = nullptr;        // the accumulation of the most recent batch: the next one's accumulation follows it
     std::vector<cudaEvent_t> event_pool;     // timing events are recycled, never created per call
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;   // render spans not yet folded into render_ms
     LaunchCfg cfg{};
@@ -247,14 +254,20 @@ void free_all(crt_ctx* c) {
     c->pending.clear();
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     c->event_pool.clear();
-    for (cudaEvent_t* e : {&c->ev0, &c->ev1, &c->ev_fork, &c->ev_join, &c->ev_order}) {
+    for (cudaEvent_t* e : {&c->ev0, &c->ev1, &c->ev_epoch, &c->ev_order}) {
         if (*e) cudaEventDestroy(*e);
         *e = nullptr;
     }
-    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
-    c->aux_stream = nullptr;
+    for (cudaStream_t& w : c->work) { if (w) cudaStreamDestroy(w); w = nullptr; }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     c->stream = nullptr;
+}
+
+// Called after every operation on c->stream that later batches must follow (see crt_ctx::work).
+int mark_epoch(crt_ctx* c) {
+    CU(cudaEventRecord(c->ev_epoch, c->stream));
+    c->epoch++;
+    return CRT_OK;
 }
 
 int check_kernel(const char* what) {
@@ -553,10 +566,10 @@ static int create_impl(const crt_scene_desc* s, uint32_t W, uint32_t H, const cr
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
-    if (c->n_slots > 1) CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    for (uint32_t si = 0; si < c->n_slots; si++) CU(cudaStreamCreateWithFlags(&c->work[si], cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
-    for (cudaEvent_t* ev : {&c->ev_fork, &c->ev_join, &c->ev_order}) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    for (cudaEvent_t* ev : {&c->ev_epoch, &c->ev_order}) CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     if (configure_kernels() != 0) return fail(CRT_ERR_CUDA, "crt_create: cannot opt in to %u KB of shared memory per CTA", 56u);
     c->cfg.sms = prop.multiProcessorCount;
     c->cfg.stream = c->stream;
@@ -608,14 +621,14 @@ static int create_impl(const crt_scene_desc* s, uint32_t W, uint32_t H, const cr
         wv.color = w.color.p;
         wv.counters = w.counters.p; wv.stats = c->stats.p; wv.capacity = (uint32_t)cap;
         w.cfg = c->cfg;
-        w.cfg.stream = si == 0 ? c->stream : c->aux_stream;
+        w.cfg.stream = c->work[si];
         CU(cudaEventCreateWithFlags(&w.accumulated, cudaEventDisableTiming));
     }
 #undef AL
     CU(cudaMemsetAsync(c->accum.p, 0, (size_t)tl.padded_pixels * sizeof(float4), c->stream));
     CU(cudaMemsetAsync(c->stats.p, 0, sizeof(DStats), c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    return CRT_OK;
+    return mark_epoch(c);
 }
 
 int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_options* opt, crt_ctx** out) {
@@ -633,21 +646,21 @@ int crt_create(const crt_scene_desc* s, uint32_t W, uint32_t H, const crt_option
 void crt_destroy(crt_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+    for (cudaStream_t w : c->work) if (w) cudaStreamSynchronize(w);
     cudaStreamSynchronize(c->stream);
     free_all(c);
     delete c;
 }
 
-// Enqueue the waves of every sample asked for so far (c->launched .. c->samples).  With two wave slots consecutive waves
-// alternate between the context's stream and the auxiliary stream: the auxiliary stream is forked from the context's
-// stream before its first wave and joined back after the last one, and the per-pixel accumulation - the only thing two
-// waves share - is chained in wave order by events, so the sums have the same bits whatever the number of slots.
+// Enqueue the waves of every sample asked for so far (c->launched .. c->samples).  Consecutive waves alternate between the
+// wave slots - across calls too - each on its slot's work stream; the per-pixel accumulation, the only thing two waves
+// share, is chained in wave order by events, so the sums have the same bits whatever the number of slots; the context's
+// stream waits for the accumulation of the call's last wave on every slot it used.
 static int launch_pending(crt_ctx* c) {
     const uint32_t spp = c->samples - c->launched;
     if (spp == 0 || c->tl.local_pixels == 0) { c->launched = c->samples; return CRT_OK; }
     const bool exact = c->flags & CRT_FLAG_EXACT_VISIT, stats = c->flags & CRT_FLAG_STATS;
-    const bool prof = c->flags & CRT_FLAG_PROFILE;
+    const bool prof = c->flags & CRT_FLAG_PROFILE;            // implies one slot (crt_create)
     cudaEvent_t a = c->take_event(), b = c->take_event();
     CU(cudaEventRecord(a, c->stream));
     struct Span { int stage; cudaEvent_t e; };
@@ -655,22 +668,21 @@ static int launch_pending(crt_ctx* c) {
     auto mark = [&](int stage) {
         if (!prof) return;
         cudaEvent_t e = c->take_event();
-        cudaEventRecord(e, c->stream);
+        cudaEventRecord(e, c->work[0]);
         spans.push_back({stage, e});
     };
-    const uint32_t n_waves = (spp + c->spp_per_wave - 1) / c->spp_per_wave;
-    const bool fork = c->n_slots > 1 && n_waves > 1;
-    if (fork) {
-        CU(cudaEventRecord(c->ev_fork, c->stream));
-        CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-    }
     uint32_t done = 0;
-    WaveSlot* prev = nullptr;
-    uint32_t slot_i = 0;
+    bool used[2] = {false, false};
     while (done < spp) {
         const uint32_t k = std::min(c->spp_per_wave, spp - done);
-        WaveSlot& w = c->slot[fork ? slot_i : 0];
+        const uint32_t si = c->next_slot;
+        WaveSlot& w = c->slot[si];
         const LaunchCfg& cfg = w.cfg;
+        if (c->waited_epoch[si] != c->epoch) {
+            CU(cudaStreamWaitEvent(cfg.stream, c->ev_epoch, 0));
+            c->waited_epoch[si] = c->epoch;
+        }
+        used[si] = true;
         CU(cudaMemsetAsync(w.counters.p, 0, sizeof(DCounters), cfg.stream));
         mark(-1);
         launch_raygen(c->sc, c->tl, w.wv, c->launched + done, k, c->seed, cfg);
@@ -684,26 +696,24 @@ static int launch_pending(crt_ctx* c) {
         }
         launch_traverse(c->sc, w.wv, -1, kMaxBounces - 1, exact, stats, cfg);
         mark(CRT_STAGE_SHADOW);
-        if (fork && prev) CU(cudaStreamWaitEvent(cfg.stream, prev->accumulated, 0));      // accumulate in wave order
+        if (c->last_accum && c->last_accum != w.accumulated) CU(cudaStreamWaitEvent(cfg.stream, c->last_accum, 0));   // accumulate in wave order
         launch_accumulate(c->tl, w.wv, c->accum.p, k, cfg);
-        if (fork) CU(cudaEventRecord(w.accumulated, cfg.stream));
+        CU(cudaEventRecord(w.accumulated, cfg.stream));
+        c->last_accum = w.accumulated;
         mark(CRT_STAGE_ACCUM);
         c->launches += 3 + 2 * kMaxBounces;
         done += k;
-        prev = &w;
-        slot_i ^= 1u;
+        c->next_slot = (si + 1) % c->n_slots;
     }
-    if (fork) {
-        CU(cudaEventRecord(c->ev_join, c->aux_stream));
-        CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    }
+    for (uint32_t si = 0; si < c->n_slots; si++)
+        if (used[si]) CU(cudaStreamWaitEvent(c->stream, c->slot[si].accumulated, 0));   // accumulate is a wave's last launch
     CU(cudaEventRecord(b, c->stream));
     c->pending.emplace_back(a, b);
     c->launched = c->samples;
     int rc = check_kernel("render wave");
     if (rc) return rc;
     if (prof) {
-        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaStreamSynchronize(c->work[0]));
         for (size_t i = 1; i < spans.size(); i++) {
             if (spans[i].stage < 0) continue;
             float ms = 0;
@@ -770,6 +780,8 @@ static int resolve_common(crt_ctx* c, const float4* src, bool gathered, uint8_t*
     c->launches++;
     rc = check_kernel("resolve");
     if (rc) return rc;
+    rc = mark_epoch(c);
+    if (rc) return rc;
     if (rgba_dst) CU(cudaMemcpyAsync(rgba_dst, c->rgba.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (f32_dst) CU(cudaMemcpyAsync(f32_dst, c->f32.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     return crt_sync(c);
@@ -802,6 +814,8 @@ int crt_resolve_local_rgba8_device(crt_ctx* c, void** d_ptr, size_t* bytes) {
     c->launches++;
     rc = check_kernel("resolve_local");
     if (rc) return rc;
+    rc = mark_epoch(c);                          // later batches must not add to the accumulator while it is being read
+    if (rc) return rc;
     *d_ptr = c->rgba_local.p;
     if (bytes) *bytes = (size_t)c->tl.padded_pixels * 4;
     return CRT_OK;
@@ -833,10 +847,10 @@ int crt_stream_wait_ctx(crt_ctx* c, void* stream) {
 int crt_ctx_wait_stream(crt_ctx* c, void* stream) {
     if (!c) return fail(CRT_ERR_INVALID, "crt_ctx_wait_stream: null ctx");
     CU(cudaSetDevice(c->device));
-    if ((cudaStream_t)stream == c->stream) return CRT_OK;
+    if ((cudaStream_t)stream == c->stream) return mark_epoch(c);
     CU(cudaEventRecord(c->ev_order, (cudaStream_t)stream));
     CU(cudaStreamWaitEvent(c->stream, c->ev_order, 0));
-    return CRT_OK;
+    return mark_epoch(c);                        // batches launched from now on follow what the caller's stream did
 }
 
 int crt_update_scene(crt_ctx* c, const crt_scene_desc* s) {
@@ -861,7 +875,7 @@ int crt_reset(crt_ctx* c) {
     CU(cudaMemsetAsync(c->accum.p, 0, (size_t)c->tl.padded_pixels * sizeof(float4), c->stream));
     c->samples = 0;
     c->launched = 0;
-    return CRT_OK;
+    return mark_epoch(c);
 }
 
 int crt_get_counters(crt_ctx* c, crt_counters* out) {

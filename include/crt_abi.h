@@ -69,9 +69,10 @@ typedef struct crt_options {
     uint32_t flags;           /* CRT_FLAG_*                                                                */
     void* stream;             /* cudaStream_t to enqueue on (NULL: a private non-blocking stream)          */
     uint32_t waves_in_flight; /* wavefront batches in flight, 1 or 2 (0 = default: 2, or 1 with CRT_FLAG_PROFILE).
-                                 With 2, consecutive batches run on two streams (the second one private) and
-                                 overlap; everything a caller can observe stays ordered on `stream`, and the
-                                 image is unchanged                                                           */
+                                 Batches run on private work streams, consecutive ones (of one call or of
+                                 consecutive calls) on alternating streams, and overlap; `stream` waits for
+                                 every call's batches, so everything a caller can observe stays ordered on it,
+                                 and the image is unchanged                                                   */
 } crt_options;
 
 #define CRT_FLAG_EXACT_VISIT 1u  /* no distance culling: visit exactly the leaves the reference visits     */

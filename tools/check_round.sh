@@ -1,12 +1,12 @@
 #!/bin/bash
-# parity of the closest-hit modes + bench lines + per-ray instruction counts of the current build
+# quick loop while changing kernels or the scheduler: the whole GPU suite, four bench lines, instructions per ray
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 O=gpurun_out/${1:-check}
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "closest_hit or bitwise or replay_is_bit_exact" 2>&1 | tail -4
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -4
 : > $O.jsonl
-for wl in cornellSphere_1080p monkeys_1080p terrain1m_1080p; do
-  steps=4; [ "$wl" = terrain1m_1080p ] && steps=2
+for wl in cornellSphere_1080p monkeys_1080p terrain1m_1080p cornell_256; do
+  steps=4; [ "$wl" = terrain1m_1080p ] && steps=2; [ "$wl" = cornell_256 ] && steps=64
   timeout 600 python bench.py --workload $wl --steps $steps --warmup 3 --no-cpu-baseline --no-configs ${BENCH_ARGS} >> $O.jsonl 2>> $O.err
 done
 python - $O.jsonl <<'PY'
@@ -16,5 +16,7 @@ for l in open(sys.argv[1]):
     print(j["config"]["workload"], j["value"], j["e2e"]["value"], j["seam_literal"]["value"], {k: round(v) for k, v in j["stage_ms"].items()}, j["clocks"]["sm_mhz"])
 PY
 tail -5 $O.err
-timeout 900 python tools/ncu_per_ray.py cornellSphere_1080p monkeys_1080p terrain1m_1080p 2>&1 | cut -c1-220 | tail -5
-cp gpurun_out/r02_traverse_per_ray.json $O.per_ray.json
+if [ -n "$PER_RAY" ]; then
+  timeout 900 python tools/ncu_per_ray.py cornellSphere_1080p monkeys_1080p terrain1m_1080p 2>&1 | cut -c1-220 | tail -5
+  cp gpurun_out/r02_traverse_per_ray.json $O.per_ray.json
+fi
