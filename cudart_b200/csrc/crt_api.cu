@@ -502,6 +502,11 @@ static int upload_scene(crt_ctx* c, const crt_scene_desc* s, uint32_t W, uint32_
     const size_t n_front = hc.n_front;                                     // the tree the render path's rays walk
     if (!(c->flags & CRT_FLAG_NO_SMEM_NODES) && (n_front <= kMaxSmemNodes || (c->flags & CRT_FLAG_SMEM_TOP_LEVELS)))
         sc.n_smem_nodes = std::min<uint32_t>((uint32_t)n_front, kMaxSmemNodes);
+    // Tile-ordered camera rays pay where the tree is large (monkeys +2 %, 1M terrain +2 %, 131k terrain +2 %) and cost about
+    // 1 % where the whole tree sits in shared memory and coherence buys nothing (the Cornell scenes):
+    // profiles/r02af_raygen_tile_order_ab.jsonl, r02z_bench_all.jsonl.  CRT_RAYGEN_BLOCK overrides (A/B measurements).
+    sc.raygen_block = n_front > kMaxSmemNodes ? 32u : 0u;
+    if (const char* e = getenv("CRT_RAYGEN_BLOCK")) sc.raygen_block = (uint32_t)atoi(e) / 8u * 8u;
     sc.tri_tight = n_tight_wide ? c->tri_tight.p : nullptr;
     sc.tri_gate = n_tight_wide ? c->tri_gate.p : nullptr;
     sc.dyn_pad = hc.dynamic_pad ? 1 : 0;

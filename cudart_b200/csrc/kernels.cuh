@@ -23,6 +23,7 @@ struct DScene {
     const uint32_t* tex_offsets;
     uint32_t n_wide, n_tris, n_mats, n_lights, n_tex, tex_texels;
     uint32_t n_smem_nodes;     // the first n_smem_nodes wide nodes (top levels, breadth-first) are staged in shared memory
+    uint32_t raygen_block;     // camera rays are queued in 8 x 4-pixel tiles inside blocks of this edge (0: plain row order)
     float lights_area;
     int coords_bounded;        // every node/triangle coordinate is finite and below 1e8 in magnitude
     // Tight BVH (host_scene.h): its wide nodes are [0, ref_root), the reference-leaf tree starts at ref_root.  Rays that

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 O=gpurun_out/${1:-check}
 timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -4
 : > $O.jsonl
-for wl in cornellSphere_1080p monkeys_1080p terrain1m_1080p cornell_256; do
+for wl in cornellSphere_1080p monkeys_1080p terrain1m_1080p cornell_4k; do
   steps=4; [ "$wl" = terrain1m_1080p ] && steps=2; [ "$wl" = cornell_256 ] && steps=64
   timeout 600 python bench.py --workload $wl --steps $steps --warmup 3 --no-cpu-baseline --no-configs ${BENCH_ARGS} >> $O.jsonl 2>> $O.err
 done
