@@ -89,6 +89,7 @@ SYMBOLS = {
                                 C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p]),
     "crt_tight_pad_mode": (C.c_int, [C.c_void_p]),
     "crt_tight_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "crt_derived_fingerprint": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64 * 2)]),
     "crt_fingerprint": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64 * 2)]),
     "crt_lane_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64 * 8)]),
     "crt_scene_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

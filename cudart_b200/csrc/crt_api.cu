@@ -138,10 +138,10 @@ struct HostSceneCache {
     bool valid = false;
     Fingerprint fp;
     std::vector<WideNode> wide;             // tight tree (if any) followed by the reference-leaf tree
-    std::vector<TriIsect> isect;
-    std::vector<TriShade> shade;
-    std::vector<TriIsect> tight_isect;      // the tight tree's triangle records, hot part (what every test reads)
-    std::vector<float4> tight_gate;         // ... and their reference-leaf boxes (read for would-be winners only)
+    RawVec<TriIsect> isect;                 // RawVec: sized once, then filled completely (host_scene.h)
+    RawVec<TriShade> shade;
+    RawVec<TriIsect> tight_isect;           // the tight tree's triangle records, hot part (what every test reads)
+    RawVec<float4> tight_gate;              // ... and their reference-leaf boxes (read for would-be winners only)
     std::vector<float4> light_boxes;
     WideStats wide_stats{};
     uint32_t n_tight_wide = 0, tight_split = 0, n_front = 0;
@@ -298,8 +298,8 @@ static int derive_host_scene(crt_ctx* c, const crt_scene_desc* s, const Fingerpr
                                           : flatten_wide(clustered.data(), (uint32_t)clustered.size(), tris, s->n_tris, wide);
         if (clustered.empty()) ref_tree.assign(nodes, nodes + s->n_nodes); else ref_tree.swap(clustered);
     });
-    std::vector<TriIsect>& isect = hc.isect;
-    std::vector<TriShade>& shade = hc.shade;
+    RawVec<TriIsect>& isect = hc.isect;
+    RawVec<TriShade>& shade = hc.shade;
     Worker rec_job([&] { make_tri_records(tris, s->n_tris, nodes, s->n_nodes, isect, shade); });
     // ---- tight per-triangle BVH in front of the reference-leaf tree (host_scene.h) ----
     TightBvh tight;
@@ -369,15 +369,20 @@ static int derive_host_scene(crt_ctx* c, const crt_scene_desc* s, const Fingerpr
         // lines instead of five, and the 32-byte gates are only touched by candidates that would win.
         hc.tight_isect.resize(tight.records.size());
         hc.tight_gate.resize(2 * tight.records.size());
-        for (size_t i = 0; i < tight.records.size(); i++) {
-            const TightRecord& r = tight.records[i];
-            TriIsect& h = hc.tight_isect[i];
-            memcpy(h.v1, r.v1, 12); h.index = r.origIdx;
-            memcpy(h.e1, r.e1, 12); h.leafFirst = r.leafFirst;
-            memcpy(h.e2, r.e2, 12); h.materialId = r.materialId;
-            hc.tight_gate[2 * i] = make_float4(r.gateLo[0], r.gateLo[1], r.gateLo[2], 0.f);
-            hc.tight_gate[2 * i + 1] = make_float4(r.gateHiX, r.gateHiY, r.gateHiZ, 0.f);
-        }
+        const TightRecord* const recs = tight.records.data();
+        TriIsect* const hot = hc.tight_isect.data();
+        float4* const gate = hc.tight_gate.data();
+        parallel_for((uint32_t)tight.records.size(), [=](uint32_t b, uint32_t e) {
+            for (uint32_t i = b; i < e; i++) {
+                const TightRecord& r = recs[i];
+                TriIsect& h = hot[i];
+                memcpy(h.v1, r.v1, 12); h.index = r.origIdx;
+                memcpy(h.e1, r.e1, 12); h.leafFirst = r.leafFirst;
+                memcpy(h.e2, r.e2, 12); h.materialId = r.materialId;
+                gate[2 * (size_t)i] = make_float4(r.gateLo[0], r.gateLo[1], r.gateLo[2], 0.f);
+                gate[2 * (size_t)i + 1] = make_float4(r.gateHiX, r.gateHiY, r.gateHiZ, 0.f);
+            }
+        });
     }
     hc.region_lo = region_lo; hc.region_hi = region_hi;
     {   // the reference leaf holding each light triangle
@@ -1017,6 +1022,39 @@ int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t
         *n_wide_out = (uint32_t)tw.size();
     }
     return (int)CRT_OK;
+    });
+}
+
+int crt_derived_fingerprint(const void* tris_, uint32_t n_tris, const void* nodes_, uint32_t n_nodes, const float* region, uint32_t pad_mode,
+                            uint64_t out[2]) {
+    if (!tris_ || !nodes_ || !region || !out || pad_mode > 2) return fail(CRT_ERR_INVALID, "crt_derived_fingerprint: bad argument");
+    return guarded("crt_derived_fingerprint", [&] {
+        const RefTriangle* tris = (const RefTriangle*)tris_;
+        const RefNode* nodes = (const RefNode*)nodes_;
+        Fingerprint fp;
+        auto mix = [&](const void* p, size_t bytes) { const uint64_t n = bytes; fingerprint_mix(fp, &n, sizeof n); fingerprint_mix(fp, p, bytes); };
+        std::vector<RefNode> clustered;
+        recluster_leaves(nodes, n_nodes, clustered);
+        mix(clustered.data(), clustered.size() * sizeof(RefNode));
+        std::vector<WideNode> wide;
+        flatten_wide(clustered.data(), (uint32_t)clustered.size(), tris, n_tris, wide);
+        mix(wide.data(), wide.size() * sizeof(WideNode));
+        RawVec<TriIsect> isect;
+        RawVec<TriShade> shade;
+        make_tri_records(tris, n_tris, nodes, n_nodes, isect, shade);
+        mix(isect.data(), isect.size() * sizeof(TriIsect));
+        mix(shade.data(), shade.size() * sizeof(TriShade));
+        TightBvh tb;
+        build_tight_bvh(tris, n_tris, nodes, n_nodes, F3{region[0], region[1], region[2]}, F3{region[3], region[4], region[5]}, (PadMode)pad_mode, tb);
+        mix(tb.nodes.data(), tb.nodes.size() * sizeof(RefNode));
+        mix(tb.records.data(), tb.records.size() * sizeof(TightRecord));
+        mix(tb.boxes.data(), tb.boxes.size() * sizeof(float));
+        wide.clear();
+        if (!tb.nodes.empty()) flatten_wide(tb.nodes.data(), (uint32_t)tb.nodes.size(), tb.tris.data(), n_tris, wide);
+        mix(wide.data(), wide.size() * sizeof(WideNode));
+        out[0] = fp.a;
+        out[1] = fp.b;
+        return (int)CRT_OK;
     });
 }
 

@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <type_traits>
 
 namespace crt {
 namespace {
@@ -35,11 +36,30 @@ struct PrimBox {          // bvh.cpp:18-30
     F3 mn, mx, center;
 };
 
-struct BuildNode {
+struct BuildNode {                      // every field is written by build(): the pool is raw, uninitialised storage
     F3 mn, mx;
-    int child0 = -1, child1 = -1;       // child0 = upper partition [mid,end), child1 = lower [start,mid)
-    uint32_t first = 0, count = 0;      // leaf payload
+    int child0, child1;                 // child0 = upper partition [mid,end), child1 = lower [start,mid)
+    uint32_t first, count;              // leaf payload (count == 0: interior node)
+    uint32_t size;                      // nodes in this subtree (what lets flatten() place subtrees independently)
 };
+
+// Subtrees of at least this many nodes / primitives get a thread of their own in the top kForkLevels levels of a tree
+// (at most 16 threads per tree).  CRT_BVH_FORK_MIN overrides the threshold: the tests force forking on the small golden
+// scenes, and switch it off on large ones, to pin that no tree depends on the number of threads.
+inline uint32_t fork_min() {
+    static const uint32_t v = [] { const char* e = getenv("CRT_BVH_FORK_MIN"); return e ? (uint32_t)std::max(8, atoi(e)) : (1u << 14); }();
+    return v;
+}
+constexpr int kForkLevels = 4;
+
+struct FreeDeleter { void operator()(void* p) const { std::free(p); } };
+template <class T>
+std::unique_ptr<T[], FreeDeleter> raw_array(size_t n) {          // uninitialised storage for trivially copyable records
+    static_assert(std::is_trivially_copyable<T>::value && std::is_trivially_destructible<T>::value, "raw_array");
+    void* p = std::malloc(std::max<size_t>(n, 1) * sizeof(T));
+    if (!p) throw std::bad_alloc();
+    return std::unique_ptr<T[], FreeDeleter>((T*)p);
+}
 
 // The tree is defined by the reference's SEQUENTIAL recursion (std::partition / std::nth_element per range, D26), but
 // the two halves of a split touch disjoint ranges of the primitive array and a leaf's triangles end up exactly where
@@ -50,15 +70,8 @@ struct BuildNode {
 struct Builder {
     const RefTriangle* src;
     std::vector<PrimBox> prims;
-    std::vector<BuildNode> pool;
+    std::unique_ptr<BuildNode[], FreeDeleter> pool;
     std::atomic<int> next_node{0};
-    // fork only for subtrees of at least this many triangles (CRT_BVH_FORK_MIN overrides it: the tests force forking on
-    // the small golden scenes) in the top levels (at most 16 threads)
-    static uint32_t fork_min() {
-        static const uint32_t v = [] { const char* e = getenv("CRT_BVH_FORK_MIN"); return e ? (uint32_t)std::max(8, atoi(e)) : (1u << 14); }();
-        return v;
-    }
-    static constexpr int kForkDepth = 4;
 
     // "volume as area" (bvh.cpp:334-337)
     static float box_measure(const F3& mn, const F3& mx) {
@@ -88,6 +101,8 @@ struct Builder {
         BuildNode& nd = pool[node];
         nd.first = start;               // == orderedTriangles.size() at this point of the reference's recursion (bvh.cpp:150-152)
         nd.count = end - start;
+        nd.child0 = nd.child1 = -1;
+        nd.size = 1;
         nd.mn = mn;
         nd.mx = mx;
         return node;
@@ -158,7 +173,7 @@ struct Builder {
             }
         }
         int lower, upper;
-        if (depth < kForkDepth && n >= fork_min()) {
+        if (depth < kForkLevels && n >= fork_min()) {
             Worker t([&, this] { lower = build(start, mid, depth + 1); });
             upper = build(mid, end, depth + 1);
             t.join();
@@ -169,27 +184,42 @@ struct Builder {
         BuildNode& nd = pool[node];
         nd.child0 = upper;                  // ... but stored second: child 0 is the upper partition
         nd.child1 = lower;
+        nd.first = nd.count = 0;
+        nd.size = 1 + pool[upper].size + pool[lower].size;
         nd.mx = hi3(pool[upper].mx, pool[lower].mx);
         nd.mn = lo3(pool[upper].mn, pool[lower].mn);
         return node;
     }
 
-    int flatten(int node, std::vector<RefNode>& out) {
-        int my = (int)out.size();
-        out.emplace_back();
-        std::memset(&out[my], 0, sizeof(RefNode));
-        out[my].mn = pool[node].mn;
-        out[my].mx = pool[node].mx;
-        if (pool[node].count > 0) {
-            out[my].offset = (int32_t)pool[node].first;
-            out[my].nTris = (int16_t)pool[node].count;
-            out[my].axis = 0;
-        } else {
-            flatten(pool[node].child0, out);
-            int second = flatten(pool[node].child1, out);
-            out[my].offset = second;
+    // The reference's pre-order layout (bvh.cpp:284-306): a node, the whole subtree of child 0, then child 1, whose index
+    // the node stores.  With the subtree sizes known every subtree's place is known, so large ones are written by their
+    // own threads.  `out` is pre-sized by the caller.
+    void flatten(int node, uint32_t my, RefNode* out, int depth = 0) const {
+        for (;;) {
+            const BuildNode& bn = pool[node];
+            RefNode& o = out[my];
+            std::memset(&o, 0, sizeof(RefNode));
+            o.mn = bn.mn;
+            o.mx = bn.mx;
+            if (bn.count > 0) {
+                o.offset = (int32_t)bn.first;
+                o.nTris = (int16_t)bn.count;
+                o.axis = 0;
+                return;
+            }
+            const uint32_t second = my + 1 + pool[bn.child0].size;
+            o.offset = (int32_t)second;
+            if (depth < kForkLevels && bn.size >= fork_min()) {
+                Worker t([&, this] { flatten(bn.child0, my + 1, out, depth + 1); });
+                flatten(bn.child1, second, out, depth + 1);
+                t.join();
+                return;
+            }
+            flatten(bn.child0, my + 1, out, depth + 1);
+            node = bn.child1;               // the second child: iterate instead of recursing
+            my = second;
+            depth++;
         }
-        return my;
     }
 };
 
@@ -198,26 +228,31 @@ struct Builder {
 void build_reference_bvh(RefTriangle* tris, const float* positions, uint32_t n, std::vector<RefNode>& nodes_out) {
     Builder b;
     b.src = tris;
-    b.prims.reserve(n);
-    for (uint32_t i = 0; i < n; i++) {            // bvh.cpp:79-96 (boxes from the three vertex positions)
-        const float* p = positions + 9 * (size_t)i;
-        F3 a{p[0], p[1], p[2]}, c{p[3], p[4], p[5]}, d{p[6], p[7], p[8]};
-        PrimBox pb;
-        pb.tri = (int)i;
-        pb.mn = {std::min(a.x, std::min(c.x, d.x)), std::min(a.y, std::min(c.y, d.y)), std::min(a.z, std::min(c.z, d.z))};
-        pb.mx = {std::max(a.x, std::max(c.x, d.x)), std::max(a.y, std::max(c.y, d.y)), std::max(a.z, std::max(c.z, d.z))};
-        pb.center = {(pb.mn.x + pb.mx.x) * 0.5f, (pb.mn.y + pb.mx.y) * 0.5f, (pb.mn.z + pb.mx.z) * 0.5f};
-        b.prims.push_back(pb);
-    }
     nodes_out.clear();
     if (n == 0) return;
-    b.pool.resize(2 * (size_t)n);
+    b.prims.resize(n);
+    PrimBox* const pbs = b.prims.data();
+    parallel_for(n, [=](uint32_t lo, uint32_t hi) {
+        for (uint32_t i = lo; i < hi; i++) {      // bvh.cpp:79-96 (boxes from the three vertex positions)
+            const float* p = positions + 9 * (size_t)i;
+            F3 a{p[0], p[1], p[2]}, c{p[3], p[4], p[5]}, d{p[6], p[7], p[8]};
+            PrimBox pb;
+            pb.tri = (int)i;
+            pb.mn = {std::min(a.x, std::min(c.x, d.x)), std::min(a.y, std::min(c.y, d.y)), std::min(a.z, std::min(c.z, d.z))};
+            pb.mx = {std::max(a.x, std::max(c.x, d.x)), std::max(a.y, std::max(c.y, d.y)), std::max(a.z, std::max(c.z, d.z))};
+            pb.center = {(pb.mn.x + pb.mx.x) * 0.5f, (pb.mn.y + pb.mx.y) * 0.5f, (pb.mn.z + pb.mx.z) * 0.5f};
+            pbs[i] = pb;
+        }
+    });
+    b.pool = raw_array<BuildNode>(2 * (size_t)n);
     int root = b.build(0, n);
-    nodes_out.reserve((size_t)b.next_node.load());
-    b.flatten(root, nodes_out);
-    std::vector<RefTriangle> ordered(n);
-    for (uint32_t i = 0; i < n; i++) ordered[i] = tris[b.prims[i].tri];
-    std::copy(ordered.begin(), ordered.end(), tris);
+    nodes_out.resize((size_t)b.pool[root].size);
+    b.flatten(root, 0, nodes_out.data());
+    auto ordered = raw_array<RefTriangle>(n);
+    RefTriangle* const ord = ordered.get();
+    const PrimBox* const prims = b.prims.data();
+    parallel_for(n, [=](uint32_t lo, uint32_t hi) { for (uint32_t i = lo; i < hi; i++) ord[i] = tris[prims[i].tri]; });
+    parallel_for(n, [=](uint32_t lo, uint32_t hi) { std::memcpy(tris + lo, ord + lo, (size_t)(hi - lo) * sizeof(RefTriangle)); });
 }
 
 void build_light_list(RefTriangle* tris, uint32_t n, float* mat_floats, const int32_t* mat_indices, uint32_t n_mats,
@@ -257,18 +292,28 @@ namespace {
 struct LeafRef { uint32_t node; F3 c; };
 
 struct Recluster {
+    // A node of the tree under construction.  Subtrees over disjoint leaf ranges are built by their own threads (nodes
+    // come from a pre-sized pool through an atomic counter); place() then writes the pre-order layout - a node, its first
+    // subtree, its second subtree - from the subtree sizes, large subtrees again on their own threads.  The tree does not
+    // depend on the number of threads: every split is a function of its own range alone.
+    struct Node { F3 mn, mx; uint32_t a, b, size, leaf; };      // a, b: children in the pool; leaf: reference node, or ~0u
     const RefNode* ref;
     std::vector<LeafRef> leaves;
-    std::vector<RefNode> out;
+    std::unique_ptr<Node[], FreeDeleter> pool;
+    std::atomic<uint32_t> next_node{0};
 
     static float area(const F3& mn, const F3& mx) {
         float dx = mx.x - mn.x, dy = mx.y - mn.y, dz = mx.z - mn.z;
         return dx * dy + dy * dz + dz * dx;
     }
-    uint32_t build(uint32_t lo, uint32_t hi) {          // [lo, hi) of `leaves`; returns index in `out`
-        const uint32_t my = (uint32_t)out.size();
-        out.emplace_back();
-        if (hi - lo == 1) { out[my] = ref[leaves[lo].node]; return my; }
+    uint32_t build(uint32_t lo, uint32_t hi, int depth = 0) {          // [lo, hi) of `leaves`; returns the pool index
+        const uint32_t my = next_node.fetch_add(1);
+        if (hi - lo == 1) {
+            Node& nd = pool[my];
+            nd.leaf = leaves[lo].node; nd.size = 1; nd.a = nd.b = 0;
+            nd.mn = ref[nd.leaf].mn; nd.mx = ref[nd.leaf].mx;
+            return my;
+        }
         F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}, cmn = mn, cmx = mx;
         for (uint32_t i = lo; i < hi; i++) {
             const RefNode& l = ref[leaves[i].node];
@@ -319,14 +364,40 @@ struct Recluster {
             mid = lo;
         }
         if (mid == lo || mid == hi) mid = (lo + hi) / 2;      // coincident centroids: split by count
-        build(lo, mid);
-        const uint32_t second = build(mid, hi);
-        RefNode& nd = out[my];
-        std::memset(&nd, 0, sizeof nd);
+        uint32_t first, second;
+        if (depth < kForkLevels && hi - lo >= fork_min()) {
+            Worker t([&, this] { first = build(lo, mid, depth + 1); });
+            second = build(mid, hi, depth + 1);
+            t.join();
+        } else {
+            first = build(lo, mid, depth + 1);
+            second = build(mid, hi, depth + 1);
+        }
+        Node& nd = pool[my];
         nd.mn = mn; nd.mx = mx;
-        nd.offset = (int32_t)second;
-        nd.nTris = 0; nd.axis = 0;
+        nd.a = first; nd.b = second; nd.leaf = 0xffffffffu;
+        nd.size = 1 + pool[first].size + pool[second].size;
         return my;
+    }
+    void place(uint32_t k, uint32_t my, RefNode* out, int depth = 0) const {
+        for (;;) {
+            const Node& nd = pool[k];
+            if (nd.leaf != 0xffffffffu) { out[my] = ref[nd.leaf]; return; }      // leaf records verbatim
+            const uint32_t second = my + 1 + pool[nd.a].size;
+            RefNode& o = out[my];
+            std::memset(&o, 0, sizeof o);
+            o.mn = nd.mn; o.mx = nd.mx;
+            o.offset = (int32_t)second;
+            o.nTris = 0; o.axis = 0;
+            if (depth < kForkLevels && nd.size >= fork_min()) {
+                Worker t([&, this] { place(nd.a, my + 1, out, depth + 1); });
+                place(nd.b, second, out, depth + 1);
+                t.join();
+                return;
+            }
+            place(nd.a, my + 1, out, depth + 1);
+            k = nd.b; my = second; depth++;
+        }
     }
 };
 }  // namespace
@@ -340,9 +411,10 @@ void recluster_leaves(const RefNode* nodes, uint32_t n_nodes, std::vector<RefNod
                                      (nodes[k].mn.z + nodes[k].mx.z) * 0.5f}});
     out.clear();
     if (rc.leaves.empty()) return;
-    rc.out.reserve(2 * rc.leaves.size());
-    rc.build(0, (uint32_t)rc.leaves.size());
-    out.swap(rc.out);
+    rc.pool = raw_array<Recluster::Node>(2 * rc.leaves.size());
+    const uint32_t root = rc.build(0, (uint32_t)rc.leaves.size());
+    out.resize(rc.pool[root].size);
+    rc.place(root, 0, out.data());
 }
 
 CullBound triangle_cull_bound(const RefTriangle& t) {
@@ -372,22 +444,26 @@ WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, const RefTriangle
     out.clear();
     if (n_nodes == 0) return st;
     // cull bound per binary node, bottom-up (children always have larger indices in the pre-order layout)
-    std::vector<CullBound> cb(n_nodes);
-    for (uint32_t k = n_nodes; k-- > 0;) {
-        const RefNode& nd = nodes[k];
-        CullBound b{1.f, 0.f};
-        if (nd.nTris > 0) {
+    RawVec<CullBound> cb(n_nodes);
+    CullBound* const cbp = cb.data();
+    parallel_for(n_nodes, [=](uint32_t lo_, uint32_t hi_) {            // the leaves (square roots per triangle): all threads
+        for (uint32_t k = lo_; k < hi_; k++) {
+            const RefNode& nd = nodes[k];
+            if (nd.nTris <= 0) continue;
+            CullBound b{1.f, 0.f};
             for (uint32_t i = 0; i < (uint32_t)(uint16_t)nd.nTris && (uint32_t)nd.offset + i < n_tris; i++) {
                 const CullBound t = triangle_cull_bound(tris[(uint32_t)nd.offset + i]);
                 b.A = std::min(b.A, t.A);
                 b.B = std::max(b.B, t.B);
             }
-        } else {
-            const CullBound &l = cb[k + 1], &r = cb[(uint32_t)nd.offset];
-            b.A = std::min(l.A, r.A);
-            b.B = std::max(l.B, r.B);
+            cbp[k] = b;
         }
-        cb[k] = b;
+    });
+    for (uint32_t k = n_nodes; k-- > 0;) {
+        const RefNode& nd = nodes[k];
+        if (nd.nTris > 0) continue;
+        const CullBound &l = cb[k + 1], &r = cb[(uint32_t)nd.offset];
+        cb[k] = {std::min(l.A, r.A), std::max(l.B, r.B)};
     }
     struct Item { uint32_t bin; uint32_t wide; uint32_t depth; };
     std::vector<Item> todo;
@@ -410,14 +486,18 @@ WideStats flatten_wide(const RefNode* nodes, uint32_t n_nodes, const RefTriangle
         return (uint32_t)out.size() - 1;
     };
 
+    out.reserve(n_nodes / 2 + 16);
+    child_cb.reserve(4 * (size_t)(n_nodes / 2 + 16));
+    todo.reserve(n_nodes / 2 + 16);
     uint32_t root = new_wide();
     todo.push_back({0, root, 1});
+    std::vector<Slot> slots;
     // breadth-first: wide-node indices grow level by level, so "the first M nodes" are the top of the tree
     // (that prefix is what the traversal kernels stage in shared memory)
     for (size_t head = 0; head < todo.size(); head++) {
         Item it = todo[head];
         st.depth = std::max(st.depth, it.depth);
-        std::vector<Slot> slots;
+        slots.clear();
         const RefNode& top = nodes[it.bin];
         auto push_leaf_chunks = [&](uint32_t bin) {
             const RefNode& lf = nodes[bin];
@@ -517,14 +597,15 @@ struct TightPrim { uint32_t first, count; F3 mn, mx, c; };     // members[first 
 struct TightBuilder {
     std::vector<TightPrim> prims;
     std::vector<uint32_t> members;               // triangle indices, grouped per primitive
-    std::vector<RefNode> out;                    // after finish(): pre-order layout (first child = index + 1, offset = second)
     std::vector<uint32_t> order;                 // tight slot -> original triangle index
     // Large subtrees are built on their own threads (disjoint primitive ranges): nodes come from a pre-sized pool
-    // through an atomic counter, a leaf's slots are known from the weight in front of it, and finish() lays the pool
-    // out in pre-order afterwards.  The result does not depend on the number of threads.
-    std::vector<RefNode> pool;
-    std::vector<int32_t> first_child;
+    // through an atomic counter, a leaf's slots are known from the weight in front of it, and place() writes the pool
+    // out in pre-order afterwards from the subtree sizes (large subtrees again on their own threads).  The result does
+    // not depend on the number of threads.
+    struct Node { F3 mn, mx; uint32_t a, b, size, first, count; };   // count > 0: leaf over slots [first, first + count)
+    std::unique_ptr<Node[], FreeDeleter> pool;
     std::atomic<uint32_t> next_node{0};
+    uint32_t root = 0;
     // Largest leaf, in triangles.  8 where a triangle test is cheap next to a node visit (static pad); 4 in the
     // dynamic-pad trees, whose leaves are far less uniform in size (the warp pass lasts as long as its longest leaf):
     // measured monkeys 1189 -> 1226, 1M terrain 602 -> 606 Msamples/s, but cornellSphere (static) 2266 -> 2048
@@ -534,28 +615,36 @@ struct TightBuilder {
     void run() {
         uint32_t total = 0;
         for (const TightPrim& p : prims) total += p.count;
-        pool.assign(2 * prims.size() + 2, RefNode{});
-        first_child.assign(pool.size(), -1);
+        pool = raw_array<Node>(2 * prims.size() + 2);
         order.assign(total, 0u);
         next_node = 0;
-        const uint32_t root = build(0, (uint32_t)prims.size(), 0, 0);
-        out.clear();
-        out.reserve(next_node.load());
-        std::vector<std::pair<uint32_t, int32_t>> todo;          // (pool node, index of the parent waiting for its second child)
-        todo.push_back({root, -1});
-        while (!todo.empty()) {
-            const auto [k, parent] = todo.back();
-            todo.pop_back();
-            const uint32_t my = (uint32_t)out.size();
-            out.push_back(pool[k]);
-            if (parent >= 0) out[(size_t)parent].offset = (int32_t)my;
-            if (pool[k].nTris <= 0) {
-                todo.push_back({(uint32_t)pool[k].offset, (int32_t)my});     // second child: after the whole first subtree
-                todo.push_back({(uint32_t)first_child[k], -1});              // first child: next in pre-order
+        root = build(0, (uint32_t)prims.size(), 0, 0);
+    }
+    uint32_t n_nodes() const { return pool[root].size; }
+    // Pre-order layout (first child = index + 1, offset = second child) of the subtree of pool node k at out[my ...];
+    // `out` is the final array: leaf offsets are shifted by slot_base (the triangles of the trees spliced in front).
+    void place(uint32_t k, uint32_t my, RefNode* out, uint32_t slot_base, int depth = 0) const {
+        for (;;) {
+            const Node& nd = pool[k];
+            RefNode& o = out[my];
+            std::memset(&o, 0, sizeof o);
+            o.mn = nd.mn; o.mx = nd.mx;
+            if (nd.count > 0) {
+                o.offset = (int32_t)(nd.first + slot_base);
+                o.nTris = (int16_t)nd.count;
+                return;
             }
+            const uint32_t second = my + 1 + pool[nd.a].size;
+            o.offset = (int32_t)second;
+            if (depth < kForkLevels && nd.size >= fork_min()) {
+                Worker t([&, this] { place(nd.a, my + 1, out, slot_base, depth + 1); });
+                place(nd.b, second, out, slot_base, depth + 1);
+                t.join();
+                return;
+            }
+            place(nd.a, my + 1, out, slot_base, depth + 1);
+            k = nd.b; my = second; depth++;
         }
-        pool.clear(); pool.shrink_to_fit();
-        first_child.clear(); first_child.shrink_to_fit();
     }
 
     static double area(const F3& mn, const F3& mx) {
@@ -573,11 +662,11 @@ struct TightBuilder {
         }
         const uint32_t n = hi - lo;
         auto make_leaf = [&]() {
-            RefNode& nd = pool[my];
-            std::memset(&nd, 0, sizeof nd);
+            Node& nd = pool[my];
             nd.mn = mn; nd.mx = mx;
-            nd.offset = (int32_t)slot_base;
-            nd.nTris = (int16_t)weight;
+            nd.a = nd.b = 0; nd.size = 1;
+            nd.first = slot_base;
+            nd.count = weight;
             uint32_t slot = slot_base;
             for (uint32_t i = lo; i < hi; i++)
                 for (uint32_t m = 0; m < prims[i].count; m++) order[slot++] = members[prims[i].first + m];
@@ -598,30 +687,44 @@ struct TightBuilder {
         const bool leaf_ok = weight <= 32767u;
         if (n == 1 || (leaf_ok && weight <= 2)) return make_leaf();
         constexpr int kBins = 16;
+        // the bins of all three axes in ONE pass over the primitives (an axis without extent gets none)
+        struct Bin { F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}; uint32_t w = 0; } bins[3][kBins];
+        float c0s[3], scales[3];
+        bool use[3];
+        for (int ax = 0; ax < 3; ax++) {
+            const float c0 = axis_of(cmn, ax), c1 = axis_of(cmx, ax);
+            use[ax] = c1 > c0;
+            c0s[ax] = c0;
+            scales[ax] = use[ax] ? kBins / (c1 - c0) : 0.f;
+        }
+        for (uint32_t i = lo; i < hi; i++) {
+            const TightPrim& p = prims[i];
+            const float cc[3] = {p.c.x, p.c.y, p.c.z};
+            for (int ax = 0; ax < 3; ax++) {
+                if (!use[ax]) continue;
+                int b = (int)((cc[ax] - c0s[ax]) * scales[ax]);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                Bin& bn = bins[ax][b];
+                bn.mn = lo3(bn.mn, p.mn); bn.mx = hi3(bn.mx, p.mx);
+                bn.w += p.count;
+            }
+        }
         int bestAxis = -1, bestSplit = 0;
         double bestCost = DBL_MAX;
         for (int ax = 0; ax < 3; ax++) {
-            const float c0 = axis_of(cmn, ax), c1 = axis_of(cmx, ax);
-            if (!(c1 > c0)) continue;
-            struct Bin { F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}; uint32_t w = 0; } bins[kBins];
-            const float scale = kBins / (c1 - c0);
-            for (uint32_t i = lo; i < hi; i++) {
-                int b = (int)((axis_of(prims[i].c, ax) - c0) * scale);
-                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-                bins[b].mn = lo3(bins[b].mn, prims[i].mn); bins[b].mx = hi3(bins[b].mx, prims[i].mx);
-                bins[b].w += prims[i].count;
-            }
+            if (!use[ax]) continue;
+            const Bin* const bx = bins[ax];
             double rightA[kBins]; uint32_t rightW[kBins];
             F3 rmn{FLT_MAX, FLT_MAX, FLT_MAX}, rmx{-FLT_MAX, -FLT_MAX, -FLT_MAX};
             uint32_t rw = 0;
             for (int b = kBins - 1; b > 0; b--) {
-                rmn = lo3(rmn, bins[b].mn); rmx = hi3(rmx, bins[b].mx); rw += bins[b].w;
+                rmn = lo3(rmn, bx[b].mn); rmx = hi3(rmx, bx[b].mx); rw += bx[b].w;
                 rightA[b] = rw ? area(rmn, rmx) : 0.0; rightW[b] = rw;
             }
             F3 lmn{FLT_MAX, FLT_MAX, FLT_MAX}, lmx{-FLT_MAX, -FLT_MAX, -FLT_MAX};
             uint32_t lw = 0;
             for (int b = 0; b < kBins - 1; b++) {
-                lmn = lo3(lmn, bins[b].mn); lmx = hi3(lmx, bins[b].mx); lw += bins[b].w;
+                lmn = lo3(lmn, bx[b].mn); lmx = hi3(lmx, bx[b].mx); lw += bx[b].w;
                 if (!lw || !rightW[b + 1]) continue;
                 const double cost = area(lmn, lmx) * lw + rightA[b + 1] * rightW[b + 1];
                 if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestSplit = b; }
@@ -631,7 +734,7 @@ struct TightBuilder {
         if (leaf_ok && weight <= kMaxLeaf && (bestAxis < 0 || bestCost + kTrav * area(mn, mx) >= area(mn, mx) * (double)weight)) return make_leaf();
         uint32_t mid = lo;
         if (bestAxis >= 0) {
-            const float c0 = axis_of(cmn, bestAxis), scale = kBins / (axis_of(cmx, bestAxis) - c0);
+            const float c0 = c0s[bestAxis], scale = scales[bestAxis];
             TightPrim* m = std::partition(prims.data() + lo, prims.data() + hi, [&](const TightPrim& p) {
                 int b = (int)((axis_of(p.c, bestAxis) - c0) * scale);
                 b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
@@ -646,7 +749,7 @@ struct TightBuilder {
         uint32_t left_weight = 0;
         for (uint32_t i = lo; i < mid; i++) left_weight += prims[i].count;
         uint32_t first, second;
-        if (depth < 4 && n >= (1u << 14)) {
+        if (depth < kForkLevels && n >= fork_min()) {
             Worker t([&, this] { first = build(lo, mid, slot_base, depth + 1); });
             second = build(mid, hi, slot_base + left_weight, depth + 1);
             t.join();
@@ -654,31 +757,14 @@ struct TightBuilder {
             first = build(lo, mid, slot_base, depth + 1);
             second = build(mid, hi, slot_base + left_weight, depth + 1);
         }
-        RefNode& nd = pool[my];
-        std::memset(&nd, 0, sizeof nd);
+        Node& nd = pool[my];
         nd.mn = mn; nd.mx = mx;
-        nd.offset = (int32_t)second;
-        first_child[my] = (int32_t)first;
+        nd.a = first; nd.b = second;
+        nd.first = nd.count = 0;
+        nd.size = 1 + pool[first].size + pool[second].size;
         return my;
     }
 };
-// fn(begin, end) over [0, n) in contiguous chunks on the host's threads (the chunks write disjoint outputs)
-template <class F>
-void parallel_for(uint32_t n, F fn) {
-    const uint32_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    const uint32_t parts = n < (1u << 15) ? 1u : hw;
-    if (parts == 1) { fn(0u, n); return; }
-    std::vector<std::unique_ptr<Worker>> th;
-    for (uint32_t p = 0; p < parts; p++) {
-        const uint32_t b = (uint32_t)((uint64_t)n * p / parts), e = (uint32_t)((uint64_t)n * (p + 1) / parts);
-        th.emplace_back(new Worker([=, &fn] { fn(b, e); }));
-    }
-    std::exception_ptr first;
-    for (auto& t : th) {
-        try { t->join(); } catch (...) { if (!first) first = std::current_exception(); }
-    }
-    if (first) std::rethrow_exception(first);
-}
 inline float round_down(double v) { float f = (float)v; return (double)f > v ? std::nextafterf(f, -INFINITY) : f; }
 inline float round_up(double v) { float f = (float)v; return (double)f < v ? std::nextafterf(f, INFINITY) : f; }
 
@@ -840,10 +926,8 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
     auto append = [&](TightBuilder& bd) {          // build bd's tree and splice it behind `nodes` / `order`
         bd.run();
         const uint32_t nbase = (uint32_t)nodes.size(), obase = (uint32_t)order.size();
-        for (RefNode nd : bd.out) {
-            if (nd.nTris > 0) nd.offset += (int32_t)obase; else nd.offset += (int32_t)nbase;
-            nodes.push_back(nd);
-        }
+        nodes.resize((size_t)nbase + bd.n_nodes());
+        bd.place(bd.root, nbase, nodes.data(), obase);
         order.insert(order.end(), bd.order.begin(), bd.order.end());
         return nbase;
     };
@@ -861,22 +945,28 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
     const uint32_t n_used = (uint32_t)order.size();          // triangles in no reference leaf are never reached: left out
     out.records.resize(n_used);
     out.tris.resize(n_used);
-    for (uint32_t slot = 0; slot < n_used; slot++) {
-        const uint32_t i = order[slot];
-        const RefTriangle& t = tris[i];
-        TightRecord& r = out.records[slot];
-        std::memset(&r, 0, sizeof r);
-        r.v1[0] = t.v1.x; r.v1[1] = t.v1.y; r.v1[2] = t.v1.z;
-        r.e1[0] = t.e1.x; r.e1[1] = t.e1.y; r.e1[2] = t.e1.z;
-        r.e2[0] = t.e2.x; r.e2[1] = t.e2.y; r.e2[2] = t.e2.z;
-        r.materialId = t.materialId;
-        r.origIdx = i;
-        const RefNode& lf = ref_nodes[leaf_of[i]];
-        r.leafFirst = (uint32_t)lf.offset;
-        r.gateLo[0] = lf.mn.x; r.gateLo[1] = lf.mn.y; r.gateLo[2] = lf.mn.z;
-        r.gateHiX = lf.mx.x; r.gateHiY = lf.mx.y; r.gateHiZ = lf.mx.z;
-        out.tris[slot] = t;
-    }
+    TightRecord* const recs = out.records.data();
+    RefTriangle* const ttris = out.tris.data();
+    const uint32_t* const ord = order.data();
+    const uint32_t* const leaf_idx = leaf_of.data();
+    parallel_for(n_used, [=](uint32_t b, uint32_t e) {
+        for (uint32_t slot = b; slot < e; slot++) {
+            const uint32_t i = ord[slot];
+            const RefTriangle& t = tris[i];
+            TightRecord& r = recs[slot];
+            std::memset(&r, 0, sizeof r);
+            r.v1[0] = t.v1.x; r.v1[1] = t.v1.y; r.v1[2] = t.v1.z;
+            r.e1[0] = t.e1.x; r.e1[1] = t.e1.y; r.e1[2] = t.e1.z;
+            r.e2[0] = t.e2.x; r.e2[1] = t.e2.y; r.e2[2] = t.e2.z;
+            r.materialId = t.materialId;
+            r.origIdx = i;
+            const RefNode& lf = ref_nodes[leaf_idx[i]];
+            r.leafFirst = (uint32_t)lf.offset;
+            r.gateLo[0] = lf.mn.x; r.gateLo[1] = lf.mn.y; r.gateLo[2] = lf.mn.z;
+            r.gateHiX = lf.mx.x; r.gateHiY = lf.mx.y; r.gateHiZ = lf.mx.z;
+            ttris[slot] = t;
+        }
+    });
 }
 
 SahCost sah_cost(const RefNode* nodes, uint32_t n_nodes, const F3& clip_lo, const F3& clip_hi) {
@@ -900,19 +990,22 @@ SahCost sah_cost(const RefNode* nodes, uint32_t n_nodes, const F3& clip_lo, cons
 }
 
 void make_tri_records(const RefTriangle* tris, uint32_t n, const RefNode* nodes, uint32_t n_nodes,
-                      std::vector<TriIsect>& isect, std::vector<TriShade>& shade) {
-    isect.assign(n, TriIsect{});
-    shade.assign(n, TriShade{});
-    for (uint32_t i = 0; i < n; i++) {
+                      RawVec<TriIsect>& isect, RawVec<TriShade>& shade) {
+    isect.resize(n);
+    shade.resize(n);
+    TriIsect* const isect_p = isect.data();
+    TriShade* const shade_p = shade.data();
+    parallel_for(n, [=](uint32_t lo_, uint32_t hi_) {
+    for (uint32_t i = lo_; i < hi_; i++) {
         const RefTriangle& t = tris[i];
-        TriIsect& a = isect[i];
+        TriIsect& a = isect_p[i];
         a.v1[0] = t.v1.x; a.v1[1] = t.v1.y; a.v1[2] = t.v1.z;
         a.e1[0] = t.e1.x; a.e1[1] = t.e1.y; a.e1[2] = t.e1.z;
         a.e2[0] = t.e2.x; a.e2[1] = t.e2.y; a.e2[2] = t.e2.z;
         a.materialId = t.materialId;
         a.index = i;
         a.leafFirst = 0xffffffffu;          // in no reference leaf (never reached by the reference traversal) until shown otherwise
-        TriShade& s = shade[i];
+        TriShade& s = shade_p[i];
         std::memset(&s, 0, sizeof s);
         s.n1[0] = t.n1.x; s.n1[1] = t.n1.y; s.n1[2] = t.n1.z;
         s.n2[0] = t.n2.x; s.n2[1] = t.n2.y; s.n2[2] = t.n2.z;
@@ -923,6 +1016,7 @@ void make_tri_records(const RefTriangle* tris, uint32_t n, const RefNode* nodes,
         s.area = t.area;
         s.materialId = t.materialId;
     }
+    });
     // The tie rule needs, per triangle, the firstTriOffset of the REFERENCE leaf holding it.
     for (uint32_t k = 0; k < n_nodes; k++) {
         if (nodes[k].nTris <= 0) continue;

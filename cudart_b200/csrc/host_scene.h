@@ -7,7 +7,11 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <exception>
+#include <memory>
+#include <new>
+#include <type_traits>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -36,6 +40,35 @@ public:
     }
     ~Worker() { if (t_.joinable()) t_.join(); }
 };
+
+// fn(begin, end) over [0, n) in contiguous chunks on the host's threads (the chunks write disjoint outputs)
+template <class F>
+inline void parallel_for(uint32_t n, F fn) {
+    const uint32_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const uint32_t parts = n < (1u << 15) ? 1u : hw;
+    if (parts == 1) { fn(0u, n); return; }
+    std::vector<std::unique_ptr<Worker>> th;
+    for (uint32_t p = 0; p < parts; p++) {
+        const uint32_t b = (uint32_t)((uint64_t)n * p / parts), e = (uint32_t)((uint64_t)n * (p + 1) / parts);
+        th.emplace_back(new Worker([=, &fn] { fn(b, e); }));
+    }
+    std::exception_ptr first;
+    for (auto& t : th) {
+        try { t->join(); } catch (...) { if (!first) first = std::current_exception(); }
+    }
+    if (first) std::rethrow_exception(first);
+}
+
+// std::vector whose resize() leaves trivially constructible elements uninitialised: the large record arrays below are
+// sized once and then filled completely by the host's threads - value-initialising 200 MB on one thread first (and
+// taking its page faults there) cost more than filling them.
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    template <class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new ((void*)p) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new ((void*)p) U(std::forward<A>(a)...); }
+};
+template <class T> using RawVec = std::vector<T, NoInitAlloc<T>>;
 
 struct F3 { float x, y, z; };
 struct F2 { float x, y; };
@@ -137,8 +170,8 @@ static_assert(sizeof(TightRecord) == 80, "tight triangle record");
 // region = box that contains every ray origin the bound is valid for (scene box united with the camera), see DESIGN.md
 struct TightBvh {
     std::vector<RefNode> nodes;             // binary tree in the reference's pre-order layout over the tight order
-    std::vector<TightRecord> records;       // triangles in tight order
-    std::vector<RefTriangle> tris;          // same order, for the cull bounds of flatten_wide
+    RawVec<TightRecord> records;            // triangles in tight order
+    RawVec<RefTriangle> tris;               // same order, for the cull bounds of flatten_wide
     std::vector<float> boxes;               // per ORIGINAL triangle index, lo.xyz hi.xyz: the box a ray must pass before the
                                             // triangle is tested (its own inflated box, or its reference leaf's exact box)
     uint32_t n_unbounded = 0;               // triangles too large for a distance bound (kept behind their reference leaf's box)
@@ -175,6 +208,6 @@ constexpr double kTightTraversalCost = 3.0;      // cost of visiting one binary 
 SahCost sah_cost(const RefNode* nodes, uint32_t n_nodes, const F3& clip_lo, const F3& clip_hi);
 
 void make_tri_records(const RefTriangle* tris, uint32_t n, const RefNode* nodes, uint32_t n_nodes,
-                      std::vector<TriIsect>& isect, std::vector<TriShade>& shade);
+                      RawVec<TriIsect>& isect, RawVec<TriShade>& shade);
 
 }  // namespace crt

@@ -69,6 +69,17 @@ def tight_bvh(tris: np.ndarray, nodes: np.ndarray, region_lo, region_hi, sah: bo
     return out + (pad, bool(dyn.value)) if pads else out
 
 
+def derived_fingerprint(tris: np.ndarray, nodes: np.ndarray, region_lo, region_hi, pad_mode: int = PAD_AUTO):
+    """128-bit hash of every array crt_create derives on the host (trees, flattenings, triangle records)."""
+    tris = np.ascontiguousarray(tris, TRIANGLE_DTYPE)
+    nodes = np.ascontiguousarray(nodes, NODE_DTYPE)
+    region = np.asarray(list(region_lo) + list(region_hi), np.float32)
+    out = (C.c_uint64 * 2)()
+    capi.check(capi.lib().crt_derived_fingerprint(tris.ctypes.data, tris.shape[0], nodes.ctypes.data, nodes.shape[0], region.ctypes.data,
+                                                  int(pad_mode), C.byref(out)))
+    return (int(out[0]), int(out[1]))
+
+
 def assemble(tris, positions, mat_floats, mat_indices, camera, tex_dims=None, tex_offsets=None, tex_data=None,
              width=0, height=0) -> FlatScene:
     """OBJ-order triangles + unscaled material table -> the flat scene the renderers consume."""

@@ -198,6 +198,12 @@ int crt_wide_bvh(const void* nodes, uint32_t n_nodes, void* wide_out, uint32_t c
 int crt_tight_bvh(const void* tris, uint32_t n_tris, const void* nodes, uint32_t n_nodes, const float* region, uint32_t pad_mode,
                   float* tri_boxes_out, float* tri_pad_out, uint32_t* dynamic_out,
                   uint32_t* n_split_out, uint32_t* n_tight_nodes_out, uint32_t* n_wide_out, double* sah_out /* 4 doubles or null */);
+/* Fingerprint (crt_fingerprint's hash) of every array crt_create derives on the host from these triangles and nodes: the
+ * re-clustered reference-leaf tree and its 4-ary flattening, the intersection / shading records, the tight BVH (nodes,
+ * records, boxes; region / pad_mode as in crt_tight_bvh) and its flattening.  Host only; the tests use it to pin that the
+ * threaded builders produce the same bytes whatever the number of threads. */
+int crt_derived_fingerprint(const void* tris, uint32_t n_tris, const void* nodes, uint32_t n_nodes, const float* region, uint32_t pad_mode,
+                            uint64_t out[2]);
 /* 0 = this context's render path does not walk the tight BVH, 1 = static pad, 2 = dynamic pad. */
 int crt_tight_pad_mode(const crt_ctx* ctx);
 /* Whether this context's render path walks the tight BVH: its wide-node count (0 = off) and individually boxed triangles. */

@@ -123,3 +123,40 @@ def test_threaded_bvh_build_is_the_sequential_tree():
         "print('ok')\n" % (root, os.path.join(root, "tests")))
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CRT_BVH_FORK_MIN="8"), capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def _derived_fingerprints_in_subprocess(fork_min):
+    """{scene: {pad mode: fingerprint}} of every host-derived array (crt_derived_fingerprint), computed in a fresh process with
+    the fork threshold of the threaded builders forced to `fork_min`: the six golden scenes plus the 131 074-triangle terrain."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json, os\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from conftest import SCENES, GOLDEN\n"
+        "from grazing import region_of\n"
+        "from cudart_b200 import scenebuild, load_crts\n"
+        "from cudart_b200.procedural import terrain_scene\n"
+        "scenes = {name: load_crts(os.path.join(GOLDEN, name + '.crts.gz')) for name in SCENES}\n"
+        "scenes['terrain256'] = terrain_scene(256, 64, 36)\n"
+        "out = {}\n"
+        "for name, fs in scenes.items():\n"
+        "    lo, hi = region_of(fs)\n"
+        "    out[name] = {str(m): scenebuild.derived_fingerprint(fs.tris, fs.nodes, lo, hi, m) for m in (1, 2)}\n"
+        "print('FP ' + json.dumps(out))\n" % (root, os.path.join(root, "tests")))
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CRT_BVH_FORK_MIN=str(fork_min)), capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return json.loads([l for l in p.stdout.splitlines() if l.startswith("FP ")][-1][3:])
+
+
+def test_derived_arrays_do_not_depend_on_the_number_of_threads():
+    """crt_create's host side (re-clustered reference-leaf tree, tight BVH, both 4-ary flattenings, triangle records) forks
+    subtrees onto threads and lays the trees out from subtree sizes.  Every byte it derives must be the same with forking
+    forced everywhere (threshold 8), at the default threshold (the terrain forks, the golden scenes do not) and with forking
+    switched off (threshold 2^30): the trees are functions of the input alone."""
+    forced, default, off = (_derived_fingerprints_in_subprocess(m) for m in (8, 1 << 14, 1 << 30))
+    assert forced == default == off
+    assert len({tuple(v["1"]) for v in forced.values()}) == len(forced)          # and the hash does tell the scenes apart
