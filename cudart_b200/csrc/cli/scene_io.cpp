@@ -5,6 +5,9 @@
 
 #include <algorithm>
 #include <array>
+#include <cerrno>
+#include <cfloat>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -220,24 +223,115 @@ void load_mtl(const std::string& path, std::vector<ObjMaterial>& out) {
 }
 }  // namespace
 
+namespace {
+// ---- fast path of load_obj ----------------------------------------------------------------------------------------
+// A 1M-triangle OBJ has 1.4 M lines; going through std::getline + token vectors + std::stof / std::stoi for each of them took
+// 1.7 s of the command line's 2.5 s before the first sample.  The lines that make up such a file have one strict shape -
+// `v x y z`, `vn x y z`, `vt u v`, `f a b c` with corners a, a/b, a//c or a/b/c, single blanks, nothing else - and are parsed
+// here straight from the file buffer.  Anything that deviates in any way (leading or doubled blanks, tabs, a trailing blank
+// or '\r', other keys, numbers that are not plain decimals, indices of more than 9 digits, out-of-range values) is NOT
+// handled: the line goes through line_slow(), the reference parser's own token rules, so quirks and error behaviour stay
+// what they were.
+
+// [sign] digits [. digits] [e [sign] digits] with at least one digit in the mantissa; returns the end or nullptr
+const char* plain_decimal_end(const char* p) {
+    if (*p == '-' || *p == '+') p++;
+    const char* d = p;
+    while (*p >= '0' && *p <= '9') p++;
+    size_t digits = (size_t)(p - d);
+    if (*p == '.') {
+        p++;
+        d = p;
+        while (*p >= '0' && *p <= '9') p++;
+        digits += (size_t)(p - d);
+    }
+    if (digits == 0) return nullptr;
+    if (*p == 'e' || *p == 'E') {
+        const char* q = p + 1;
+        if (*q == '-' || *q == '+') q++;
+        if (!(*q >= '0' && *q <= '9')) return nullptr;
+        while (*q >= '0' && *q <= '9') q++;
+        p = q;
+    }
+    return p;
+}
+// n plain decimals separated by single blanks, ending exactly at `end`; the values std::stof would return (stof is strtof
+// plus error checks: out-of-range results make the caller fall back to it)
+bool parse_floats(const char* p, const char* end, float* dst, int n) {
+    for (int k = 0; k < n; k++) {
+        const char* e = plain_decimal_end(p);
+        if (!e || e > end) return false;
+        if (k + 1 < n ? (*e != ' ') : (e != end)) return false;
+        // std::from_chars and strtof are both correctly rounded, so they agree wherever the result is an ordinary number
+        // (checked on 2e7 random decimals); zeros, subnormals and overflows take strtof, whose ERANGE is stof's exception
+        float v = 0.f;
+        const std::from_chars_result r = std::from_chars(p, e, v);
+        if (r.ec != std::errc() || r.ptr != e || !(std::fabs(v) >= FLT_MIN) || !std::isfinite(v)) {
+            errno = 0;
+            char* stop = nullptr;
+            v = std::strtof(p, &stop);
+            if (stop != e || errno == ERANGE) return false;
+        }
+        dst[k] = v;
+        p = e + 1;
+    }
+    return true;
+}
+// [-] 1..9 digits: what std::stoi returns for such a token
+const char* parse_index(const char* p, int& out) {
+    const bool neg = *p == '-';
+    if (neg) p++;
+    const char* d = p;
+    int v = 0;
+    while (*p >= '0' && *p <= '9' && p - d < 10) v = v * 10 + (*p++ - '0');
+    if (p == d || p - d > 9) return nullptr;
+    out = neg ? -v : v;
+    return p;
+}
+template <class T>
+const T* element_or_null(const std::vector<T>& v, int idx) {          // element_at without the throw
+    idx = idx < 0 ? (int)v.size() + idx : idx - 1;
+    return (idx < 0 || idx >= (int)v.size()) ? nullptr : &v[(size_t)idx];
+}
+}  // namespace
+
 ObjFile load_obj(const std::string& path) {
     ObjFile out;
     if (path.size() < 4 || path.substr(path.size() - 4) != ".obj") die("Failed to load mesh for " + path);
-    std::ifstream f(path);
-    if (!f.is_open()) die("Failed to load mesh for " + path);
+    std::string text;
+    {
+        std::ifstream f(path, std::ios::binary);
+        if (!f.is_open()) die("Failed to load mesh for " + path);
+        f.seekg(0, std::ios::end);
+        const std::streamoff size = f.tellg();
+        f.seekg(0, std::ios::beg);
+        text.resize(size > 0 ? (size_t)size : 0);
+        if (size > 0) f.read(&text[0], size);
+        text.resize((size_t)std::max<std::streamsize>(f.gcount(), 0));
+    }
     std::vector<std::array<float, 3>> pos, nor;
     std::vector<std::array<float, 2>> tex;
     std::vector<std::string> mesh_mat_names;
     std::vector<ObjVertex> cur;
     std::string meshname, line;
     bool listening = false;
+    {   // three vertices per `f` line: size the vertex soup once instead of growing 96 MB arrays by doubling
+        size_t faces = 0;
+        for (size_t i = 0; i + 1 < text.size(); i++)
+            if (text[i] == 'f' && text[i + 1] == ' ' && (i == 0 || text[i - 1] == '\n')) faces++;
+        out.all_vertices.reserve(3 * faces);
+        cur.reserve(3 * faces);
+    }
     auto close_mesh = [&](const std::string& name) {
         ObjMesh m;
         m.name = name;
+        const size_t left = cur.capacity() - cur.size();
         m.vertices.swap(cur);
+        cur.reserve(left);
         out.meshes.push_back(std::move(m));
     };
-    while (std::getline(f, line)) {
+    // the reference parser's rules, line by line (obj_load.h:441-723)
+    auto line_slow = [&](const std::string& line) {
         const std::string key = first_token(line);
         if (key == "o" || key == "g" || (!line.empty() && line[0] == 'g')) {
             const std::string name = (key == "o" || key == "g") ? tail_of(line) : "unnamed";
@@ -285,6 +379,85 @@ ObjFile load_obj(const std::string& path) {
             const size_t slash = path.find_last_of('/');
             load_mtl((slash == std::string::npos ? std::string() : path.substr(0, slash + 1)) + tail_of(line), out.materials);
         }
+    };
+    // the same four line kinds in their strict form, straight from the buffer; false = not handled, nothing changed
+    auto line_fast = [&](const char* b, const char* e) -> bool {
+        if (e - b < 3) return false;
+        float x[3];
+        if (b[0] == 'v' && b[1] == ' ') {
+            if (!parse_floats(b + 2, e, x, 3)) return false;
+            pos.push_back({x[0], x[1], x[2]});
+            return true;
+        }
+        if (b[0] == 'v' && b[1] == 'n' && b[2] == ' ') {
+            if (!parse_floats(b + 3, e, x, 3)) return false;
+            nor.push_back({x[0], x[1], x[2]});
+            return true;
+        }
+        if (b[0] == 'v' && b[1] == 't' && b[2] == ' ') {
+            if (!parse_floats(b + 3, e, x, 2)) return false;
+            tex.push_back({x[0], x[1]});
+            return true;
+        }
+        if (b[0] == 'f' && b[1] == ' ') {
+            ObjVertex v[3];
+            bool no_normal = false;
+            const char* p = b + 2;
+            for (int k = 0; k < 3; k++) {
+                int ip = 0, it = 0, in = 0;
+                bool has_t = false, has_n = false;
+                if (!(p = parse_index(p, ip))) return false;
+                if (*p == '/') {
+                    p++;
+                    if (*p == '/') {                                  // a//c
+                        p++;
+                        if (!(p = parse_index(p, in))) return false;
+                        has_n = true;
+                    } else {                                          // a/b or a/b/c
+                        if (!(p = parse_index(p, it))) return false;
+                        has_t = true;
+                        if (*p == '/') {
+                            p++;
+                            if (!(p = parse_index(p, in))) return false;
+                            has_n = true;
+                        }
+                    }
+                }
+                if (k < 2 ? (*p != ' ') : (p != e)) return false;
+                p++;
+                const auto* pp = element_or_null(pos, ip);
+                const auto* tp = has_t ? element_or_null(tex, it) : nullptr;
+                const auto* np = has_n ? element_or_null(nor, in) : nullptr;
+                if (!pp || (has_t && !tp) || (has_n && !np)) return false;      // the slow path reports the bad index
+                std::memcpy(v[k].p, pp->data(), 12);
+                if (tp) { v[k].t[0] = (*tp)[0]; v[k].t[1] = (*tp)[1]; }
+                if (np) std::memcpy(v[k].n, np->data(), 12);
+                else no_normal = true;
+            }
+            if (no_normal) {          // face normal from the corner positions (obj_load.h:836-847)
+                const float a[3] = {v[0].p[0] - v[1].p[0], v[0].p[1] - v[1].p[1], v[0].p[2] - v[1].p[2]};
+                const float c[3] = {v[2].p[0] - v[1].p[0], v[2].p[1] - v[1].p[1], v[2].p[2] - v[1].p[2]};
+                const float n[3] = {a[1] * c[2] - a[2] * c[1], a[2] * c[0] - a[0] * c[2], a[0] * c[1] - a[1] * c[0]};
+                for (auto& vv : v) std::memcpy(vv.n, n, 12);
+            }
+            for (auto& vv : v) { cur.push_back(vv); out.all_vertices.push_back(vv); }
+            return true;
+        }
+        return false;
+    };
+    // std::getline's view of the file: lines end at '\n', a last line without one still counts, no empty line after a
+    // final '\n'.  (The buffer is NUL-terminated, so the number parsers above stop at the latest there.)
+    const bool only_slow = getenv("CRT_OBJ_SLOW") != nullptr;      // tests: every line through the reference parser's rules
+    const char* const base = text.c_str();
+    const char* const file_end = base + text.size();
+    for (const char* b = base; b < file_end;) {
+        const char* e = (const char*)std::memchr(b, '\n', (size_t)(file_end - b));
+        if (!e) e = file_end;
+        if (only_slow || !line_fast(b, e)) {
+            line.assign(b, e);
+            line_slow(line);
+        }
+        b = e + 1;
     }
     if (!cur.empty()) close_mesh(meshname);
     // mesh i takes the material named by the i-th `usemtl` (obj_load.h:698-713, D25)
@@ -477,11 +650,10 @@ SceneArrays assemble_scene(const ObjFile& obj, const crt::RefCamera& cam, const 
 
     size_t n_tris = 0;
     for (const ObjMesh& m : obj.meshes) n_tris += m.vertices.size() / 3;
-    s.tris.resize(n_tris);
-    std::memset(s.tris.data(), 0, n_tris * sizeof(crt::RefTriangle));
-    std::vector<float> positions;
-    positions.reserve(9 * n_tris);
-    uint32_t tri_id = 0;
+    s.tris.resize(n_tris);                                  // value-initialised: every byte zero, padding included
+    if (obj.all_vertices.size() != 3 * n_tris) die("internal: vertex soup and triangle count disagree");
+    std::vector<float> positions(9 * n_tris);
+    uint32_t tri_base = 0;
     for (const ObjMesh& m : obj.meshes) {
         const Mat mm = from_mtl(m.material);
         const auto it = std::find_if(lookup.begin(), lookup.end(), [&](const Mat& x) { return ref_equal(x, mm); });
@@ -492,21 +664,32 @@ SceneArrays assemble_scene(const ObjFile& obj, const crt::RefCamera& cam, const 
             if (tf != tex_files.end()) table[mat_id].tex = (int)(tf - tex_files.begin());
         }
         s.mesh_report.emplace_back(m.name, m.vertices.size());
-        for (size_t i = 0; i + 2 < m.vertices.size(); i += 3) {       // scene.cpp:106-134
-            const ObjVertex &a = m.vertices[i], &b = m.vertices[i + 1], &c = m.vertices[i + 2];
-            crt::RefTriangle& t = s.tris[tri_id];
-            t.v1 = {a.p[0], a.p[1], a.p[2]};
-            t.n1 = {a.n[0], a.n[1], a.n[2]}; t.n2 = {b.n[0], b.n[1], b.n[2]}; t.n3 = {c.n[0], c.n[1], c.n[2]};
-            t.uv1 = {a.t[0], a.t[1]}; t.uv2 = {b.t[0], b.t[1]}; t.uv3 = {c.t[0], c.t[1]};
-            t.e1 = {b.p[0] - a.p[0], b.p[1] - a.p[1], b.p[2] - a.p[2]};
-            t.e2 = {c.p[0] - a.p[0], c.p[1] - a.p[1], c.p[2] - a.p[2]};
-            t.materialId = mat_id;
-            t.area = len3(cross3(t.e1, t.e2)) / 2.0f;
-            t.triId = tri_id++;
-        }
+        const uint32_t n_mesh = (uint32_t)(m.vertices.size() / 3);
+        const ObjVertex* const mv = m.vertices.data();
+        crt::RefTriangle* const out_tris = s.tris.data() + tri_base;
+        crt::parallel_for(n_mesh, [=](uint32_t lo, uint32_t hi) {       // scene.cpp:106-134, every triangle on its own
+            for (uint32_t k = lo; k < hi; k++) {
+                const ObjVertex &a = mv[3 * (size_t)k], &b = mv[3 * (size_t)k + 1], &c = mv[3 * (size_t)k + 2];
+                crt::RefTriangle& t = out_tris[k];
+                t.v1 = {a.p[0], a.p[1], a.p[2]};
+                t.n1 = {a.n[0], a.n[1], a.n[2]}; t.n2 = {b.n[0], b.n[1], b.n[2]}; t.n3 = {c.n[0], c.n[1], c.n[2]};
+                t.uv1 = {a.t[0], a.t[1]}; t.uv2 = {b.t[0], b.t[1]}; t.uv3 = {c.t[0], c.t[1]};
+                t.e1 = {b.p[0] - a.p[0], b.p[1] - a.p[1], b.p[2] - a.p[2]};
+                t.e2 = {c.p[0] - a.p[0], c.p[1] - a.p[1], c.p[2] - a.p[2]};
+                t.materialId = mat_id;
+                t.area = len3(cross3(t.e1, t.e2)) / 2.0f;
+                t.triId = tri_base + k;
+            }
+        });
+        tri_base += n_mesh;
     }
-    for (const ObjVertex& v : obj.all_vertices) positions.insert(positions.end(), v.p, v.p + 3);
-    if (positions.size() != 9 * n_tris) die("internal: vertex soup and triangle count disagree");
+    {
+        const ObjVertex* const av = obj.all_vertices.data();
+        float* const pp = positions.data();
+        crt::parallel_for((uint32_t)obj.all_vertices.size(), [=](uint32_t lo, uint32_t hi) {
+            for (uint32_t i = lo; i < hi; i++) std::memcpy(pp + 3 * (size_t)i, av[i].p, 12);
+        });
+    }
 
     s.mat_floats.resize(12 * (size_t)s.n_mats);
     s.mat_indices.resize(2 * (size_t)s.n_mats);

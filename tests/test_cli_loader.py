@@ -68,3 +68,111 @@ def test_cli_surface(tmp_path):
     if not torch.cuda.is_available():
         p, _ = run_cli(tmp_path, os.path.join(ROOT, "tests", "golden", "tiny"), "tiny", 8, 8)
         assert p.returncode == 1 and "no CPU fallback" in p.stderr
+
+
+QUIRKY_HEAD = """mtllib quirky.mtl
+o first
+v 0 0 0
+v 1 0 0
+v 0 1 0
+v 1.5 1.25 -0.75
+v -2.500000 3.250000 1e-3
+v +4 5E+1 -6.5e-2
+v  7 8 9
+v\t1 2 3
+v 1 2 3 
+v 0.000000 -0.000000 -0
+v 1e-42 0.1 0.2
+v 123456789012345678901234567890 1 1
+v 3.4028235e38 1.17549435e-38 16777217
+vn 0 0 1
+vn 0.0 1.0 0.0
+vt 0.25 0.75
+vt 1 0 0
+usemtl red
+f 1 2 3
+f 1/1/1 2/2/2 3/1/1
+f 1//1 2//2 3//1
+f 1/1 2/2 3/1
+f -1 -2 -3
+f 4 5 6
+f  1 2 3
+f 1 2 3 
+f 1/ 2/ 3/
+g second
+usemtl green
+f 7 8 9
+f 10 9 8
+f 0000000001 2 3
+f 6 8 10
+"""
+QUIRKY_MTL = """newmtl red
+Kd 0.8 0.1 0.1
+Ka 1 1 1
+type EMISSIVE
+newmtl green
+Kd 0.1 0.8 0.1
+"""
+QUIRKY_CAMERA = ('{"fStop": 1000.0, "eye": [0.0, 0.0, 5.0], "focalLength": 0.032, "fieldOfView": 60.0, '
+                 '"upDirection": [0.0, 1.0, 0.0], "viewDirection": [0.0, 0.0, -5.0]}')
+
+
+def _quirky_assets(tmp_path, obj_text, crlf=False):
+    a = tmp_path / "assets"
+    for d in ("meshes", "settings", "textures"):
+        (a / d).mkdir(parents=True, exist_ok=True)
+    (a / "meshes" / "quirky.obj").write_bytes(obj_text.replace("\n", "\r\n").encode() if crlf else obj_text.encode())
+    (a / "meshes" / "quirky.mtl").write_text(QUIRKY_MTL)
+    (a / "settings" / "quirky-camera.json").write_text(QUIRKY_CAMERA)
+    return str(a)
+
+
+def _run_both_parsers(tmp_path, assets):
+    res = []
+    for slow in (False, True):
+        (tmp_path / "build").mkdir(exist_ok=True)
+        (tmp_path / ".env").write_text("MESHES_PATH=%s/meshes\nCAMERA_PATH=%s/settings\nTEXTURES_PATH=%s/textures\n" % (assets, assets, assets))
+        out = tmp_path / ("quirky_%d.crts" % slow)
+        env = dict(os.environ)
+        env.pop("CRT_OBJ_SLOW", None)
+        if slow:
+            env["CRT_OBJ_SLOW"] = "1"
+        p = subprocess.run([CLI, "-f", "quirky", "-s", "1", "-w", "16", "-h", "12", "--dump-scene", str(out), "--no-render"],
+                           cwd=tmp_path / "build", capture_output=True, text=True, env=env)
+        res.append((p.returncode, p.stdout.replace(str(out), "OUT"), p.stderr, out.read_bytes() if out.exists() else None))
+    return res
+
+
+def test_fast_obj_lines_follow_the_reference_parsers_rules(tmp_path):
+    """load_obj parses the strict common form of v / vn / vt / f lines straight from the file buffer and sends everything else
+    through the reference parser's token rules.  On text full of near misses - doubled blanks, tabs, trailing blanks, '+' signs,
+    exponents, signed zeros, subnormal and overflowing numbers, `a/b`, `a//c`, `a/`, negative and zero-padded indices - the
+    scene must be byte-identical to the one obtained with EVERY line on the slow path (CRT_OBJ_SLOW), and so must the outcome
+    (exit code, messages) when a line is an error."""
+    import random
+    lines = QUIRKY_HEAD.splitlines()
+    # 1. every prefix that ends in a face (some stop at lines the reference parser rejects: both parsers must fail alike)
+    cases = ["\n".join(lines[:k]) + "\n" for k in range(20, len(lines) + 1)]
+    # 2. the error lines dropped: a file that loads
+    good = [l for l in lines if not (l.startswith("v  7") or l.startswith("v 1e-42") or l.startswith("v 1234567890123") or l.startswith("f  1")
+                                     or l == "f 1 2 3 " or l.startswith("f 0000000001"))]
+    cases += ["\n".join(good) + "\n", "\n".join(good)]                       # with and without the final newline
+    # 3. shuffled faces over the same vertices, and an out-of-range index
+    rng = random.Random(5)
+    faces = [l for l in good if l.startswith("f ")]
+    head = [l for l in good if not l.startswith("f ") and not l.startswith("g ") and not l.startswith("usemtl green")]
+    for _ in range(4):
+        rng.shuffle(faces)
+        cases.append("\n".join(head + faces) + "\n")
+    cases.append("\n".join(head + faces + ["f 1 2 99"]) + "\n")
+    cases.append("\n".join(head + faces + ["f 1 2 -99"]) + "\n")
+    loaded = 0
+    for k, text in enumerate(cases):
+        for crlf in ((False, True) if k % 7 == 0 else (False,)):
+            d = tmp_path / ("case%d_%d" % (k, crlf))
+            d.mkdir()
+            fast, slow = _run_both_parsers(d, _quirky_assets(d, text, crlf))
+            assert fast[:3] == slow[:3], (k, crlf, text, fast[:3], slow[:3])
+            assert fast[3] == slow[3], (k, crlf)
+            loaded += fast[0] == 0 and fast[3] is not None
+    assert loaded >= 6
