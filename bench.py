@@ -416,7 +416,11 @@ def measure_workload(h, workload, steps, warmup, spp_step, full=True):
     samples = float(W) * H * spp_step * steps
 
     # ---- value: scene resident, no profiling flag, device-only step ----
+    t_create = time.perf_counter()
     r = h.renderer(fs, W, H, total_spp)
+    # crt_create as the caller sees it: validation, fingerprint, the host-side derivation of the trees and records on the
+    # host's threads, device allocations and the enqueued uploads
+    out["create_s"] = round(time.perf_counter() - t_create, 4)
     # warm-up: at least `warmup` steps AND at least 0.3 s of work (a 256x256 step lasts 2 ms: three of them would leave
     # the clocks of a cold GPU still ramping)
     t_w, n_w = time.perf_counter(), 0
@@ -569,7 +573,7 @@ def main():
                 c = measure_workload(h, wl, 3, 3, args.spp_per_step, full=False)
                 configs[wl] = {"value": round(c["value"], 3), "unit": "Msamples/s", "mrays_per_s": round(c["mrays_per_s"], 3),
                                "ms_per_step": round(c["ms_per_step"], 3), "spp_per_step": c["spp_per_step"], "steps": 3,
-                               "tight_bvh": c["tight_bvh"], "scaling": "n/a (1 GPU)"}
+                               "tight_bvh": c["tight_bvh"], "create_s": c["create_s"], "scaling": "n/a (1 GPU)"}
         else:
             # BASELINE config 5 under STRONG scaling: the fixed 3840x2160 frame, 64 spp of the whole frame per step, shared
             # by the N ranks, RGBA8 gather to rank 0 every step
@@ -634,6 +638,7 @@ def main():
             "time_to_full_spp_s": m.get("time_to_full_spp_s"),
             "time_to_512spp_s": (m.get("time_to_full_spp_s") or {}).get("seconds") if total_spp == 512 else None,
             "gpu_launches": m["gpu_launches"],
+            "create_s": m["create_s"],
             "stage_ms": m["stage_ms"],
             "tight_bvh": dict(m["tight_bvh"], per_ray=m.get("per_ray")),
             "lane_stats": m.get("lane_stats"),
