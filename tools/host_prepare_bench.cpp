@@ -47,7 +47,8 @@ static void time_records(void (*fn)(const RefTriangle*, uint32_t, const RefNode*
     B shade;
     const double t0 = now();
     fn(tris.data(), (uint32_t)tris.size(), nodes.data(), (uint32_t)nodes.size(), isect, shade);
-    phase("make_tri_records", now() - t0, print, hex(fnv(isect.data(), isect.size() * 48)) + " " + hex(fnv(shade.data(), shade.size() * 80)));
+    const double dt = now() - t0;
+    phase("make_tri_records", dt, print, hex(fnv(isect.data(), isect.size() * 48)) + " " + hex(fnv(shade.data(), shade.size() * 80)));
 }
 
 static void run(const std::string& dir, bool print) {
@@ -55,9 +56,10 @@ static void run(const std::string& dir, bool print) {
     const auto pos = read_all<float>(dir + "/positions.bin");
     const uint32_t nt = (uint32_t)tris.size();
     std::vector<RefNode> nodes;
-    double t0 = now();
+    double dt, t0 = now();
     build_reference_bvh(tris.data(), pos.data(), nt, nodes);              // reorders tris into BVH order
-    phase("build_reference_bvh", now() - t0, print, "nodes " + std::to_string(nodes.size()) + " " + hex(fnv(nodes.data(), nodes.size() * 32)) + " " + hex(fnv(tris.data(), tris.size() * 128)));
+    dt = now() - t0;
+    phase("build_reference_bvh", dt, print, "nodes " + std::to_string(nodes.size()) + " " + hex(fnv(nodes.data(), nodes.size() * 32)) + " " + hex(fnv(tris.data(), tris.size() * 128)));
     // the region crt_create would use: every vertex and the terrain camera's eye, grown by 5 % of the diagonal
     F3 lo{FLT_MAX, FLT_MAX, FLT_MAX}, hi{-FLT_MAX, -FLT_MAX, -FLT_MAX};
     auto grow = [&](double x, double y, double z) {
@@ -77,24 +79,29 @@ static void run(const std::string& dir, bool print) {
     t0 = now();
     std::vector<RefNode> clustered;
     recluster_leaves(nodes.data(), (uint32_t)nodes.size(), clustered);
-    phase("recluster_leaves", now() - t0, print, hex(fnv(clustered.data(), clustered.size() * 32)));
+    dt = now() - t0;
+    phase("recluster_leaves", dt, print, hex(fnv(clustered.data(), clustered.size() * 32)));
     std::vector<WideNode> wide;
     t0 = now();
     const WideStats ws = flatten_wide(clustered.data(), (uint32_t)clustered.size(), tris.data(), nt, wide);
-    phase("flatten_wide (ref)", now() - t0, print, "wide " + std::to_string(ws.n_wide) + " depth " + std::to_string(ws.depth) + " " + hex(fnv(wide.data(), wide.size() * 128)));
+    dt = now() - t0;
+    phase("flatten_wide (ref)", dt, print, "wide " + std::to_string(ws.n_wide) + " depth " + std::to_string(ws.depth) + " " + hex(fnv(wide.data(), wide.size() * 128)));
     time_records(&make_tri_records, tris, nodes, print);
     TightBvh tb;
     t0 = now();
     build_tight_bvh(tris.data(), nt, nodes.data(), (uint32_t)nodes.size(), lo, hi, kPadAuto, tb);
-    phase("build_tight_bvh", now() - t0, print, "nodes " + std::to_string(tb.nodes.size()) + " split " + std::to_string(tb.n_split) + (tb.dynamic_pad ? " dynamic " : " static ") +
+    dt = now() - t0;
+    phase("build_tight_bvh", dt, print, "nodes " + std::to_string(tb.nodes.size()) + " split " + std::to_string(tb.n_split) + (tb.dynamic_pad ? " dynamic " : " static ") +
           hex(fnv(tb.nodes.data(), tb.nodes.size() * 32)) + " " + hex(fnv(tb.records.data(), tb.records.size() * 80)) + " " + hex(fnv(tb.boxes.data(), tb.boxes.size() * 4)));
     t0 = now();
     const SahCost a = sah_cost(tb.nodes.data(), (uint32_t)tb.nodes.size(), lo, hi), b = sah_cost(clustered.data(), (uint32_t)clustered.size(), lo, hi);
-    phase("sah_cost x 2", now() - t0, print, std::to_string(a.nodes) + " " + std::to_string(a.tris) + " / " + std::to_string(b.nodes) + " " + std::to_string(b.tris));
+    dt = now() - t0;
+    phase("sah_cost x 2", dt, print, std::to_string(a.nodes) + " " + std::to_string(a.tris) + " / " + std::to_string(b.nodes) + " " + std::to_string(b.tris));
     std::vector<WideNode> tw;
     t0 = now();
     const WideStats ts = flatten_wide(tb.nodes.data(), (uint32_t)tb.nodes.size(), tb.tris.data(), nt, tw);
-    phase("flatten_wide (tight)", now() - t0, print, "wide " + std::to_string(ts.n_wide) + " depth " + std::to_string(ts.depth) + " " + hex(fnv(tw.data(), tw.size() * 128)));
+    dt = now() - t0;
+    phase("flatten_wide (tight)", dt, print, "wide " + std::to_string(ts.n_wide) + " depth " + std::to_string(ts.depth) + " " + hex(fnv(tw.data(), tw.size() * 128)));
 }
 
 int main(int argc, char** argv) {
