@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <memory>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -272,12 +273,24 @@ int main(int argc, char* argv[]) {
          << "Camera path: " << cameraPath << endl
          << "Output: " << outFile << endl;
 
+    // CRT_CLI_TIMING=1: wall time of every phase on stderr (where the time to the image goes; not part of the reference's surface)
+    const bool timing = getenv("CRT_CLI_TIMING") != nullptr;
+    auto phase_start = high_resolution_clock::now();
+    auto phase = [&](const char* name) {
+        const auto now = high_resolution_clock::now();
+        if (timing) cerr << "[timing] " << name << " " << duration_cast<microseconds>(now - phase_start).count() / 1e6 << " s" << endl;
+        phase_start = now;
+    };
     SceneArrays scene;
     try {
         cout << "Loading single .obj as scene from " << objPath << endl;
-        const ObjFile obj = load_obj(objPath);
+        ObjFile obj = load_obj(objPath);
+        phase("load_obj");
         const crt::RefCamera cam = load_camera_json(cameraPath, (unsigned)width, (unsigned)height);
         scene = assemble_scene(obj, cam, texturePath);
+        phase("assemble_scene (triangles, materials, textures, reference BVH, light list)");
+        obj = ObjFile();
+        phase("free the OBJ vertex soup");
     } catch (const exception& e) {
         fatal(string("terminate called after throwing an instance of 'std::runtime_error'\n  what():  ") + e.what());
     }
@@ -289,17 +302,24 @@ int main(int argc, char* argv[]) {
     if (!dumpScene.empty()) save_crts(dumpScene, scene, (unsigned)width, (unsigned)height);
     if (noRender) return 0;
 
+    phase_start = high_resolution_clock::now();
     int devices = 0;
     cudaGetDeviceCount(&devices);
+    phase("CUDA driver initialisation (cudaGetDeviceCount)");
     cout << "Got " << devices << " CUDA-capable devices" << endl;
     if (devices == 0) fatal("no CUDA device: the B200 path has no CPU fallback (use --cpu for the reference's own CPU renderer)");
     gpus = max(1, min(gpus, devices));
 
-    B200Renderer renderer(scene, (unsigned)width, (unsigned)height, (unsigned)samples, gpus);
+    phase_start = high_resolution_clock::now();
+    unique_ptr<B200Renderer> renderer_owner(new B200Renderer(scene, (unsigned)width, (unsigned)height, (unsigned)samples, gpus));
+    B200Renderer& renderer = *renderer_owner;
+    phase("renderer (CUDA context, crt_create: derive + upload)");
     auto start = high_resolution_clock::now();
     launch(renderer, (unsigned)max(progress, 0), outFile, (unsigned)max(stopAfterProgress, 0));
     auto stop = high_resolution_clock::now();
+    phase("render + read-back");
     write_png_rgba8(outFile, renderer.h_img.data(), (unsigned)width, (unsigned)height);     // Launcher::saveToImage
+    phase("write PNG");
 
     const float elapsedTime = duration_cast<microseconds>(stop - start).count() / 1000000.0f;
     const int samplesRendered = renderer.getSamplesRendered();
@@ -314,5 +334,8 @@ int main(int argc, char* argv[]) {
           << ", \"mrays_per_s\": " << (c.extend_rays + c.shadow_rays) / elapsedTime / 1e6 << ", \"kernel_launches\": " << c.kernel_launches
           << ", \"device_render_ms\": " << c.render_ms << "}" << endl;
     }
+    phase_start = high_resolution_clock::now();
+    renderer_owner.reset();
+    phase("teardown (crt_destroy: device buffers, streams, page-locked staging)");
     return 0;
 }

@@ -176,3 +176,56 @@ def test_fast_obj_lines_follow_the_reference_parsers_rules(tmp_path):
             assert fast[3] == slow[3], (k, crlf)
             loaded += fast[0] == 0 and fast[3] is not None
     assert loaded >= 6
+
+
+def test_png_writer_bands_decode_to_the_same_pixels(tmp_path):
+    """write_png_rgba8 deflates the image in bands of rows on all host threads and splices the bands into ONE zlib stream
+    (cli/scene_io.cpp).  The file must decode - chunk CRCs, Adler-32 and all - to exactly the pixels handed in, for sizes with
+    one band, many bands, ragged last bands and rows wider than a band, and its bytes must not depend on how many CPUs the
+    process may use."""
+    import shutil
+    import struct
+    import zlib
+    src = tmp_path / "png_main.cpp"
+    src.write_text(r'''
+#include "cli/scene_io.h"
+#include <cstdio>
+#include <cstdlib>
+int main(int argc, char** argv) {
+    const unsigned w = (unsigned)atoi(argv[1]), h = (unsigned)atoi(argv[2]);
+    std::vector<uint8_t> img((size_t)w * h * 4);
+    uint32_t s = 12345u + w * 31u + h;
+    for (size_t i = 0; i < img.size(); i++) { s = s * 1664525u + 1013904223u; img[i] = (i % 4 == 3) ? 255 : (uint8_t)(((i / 4) % w) / 3 + ((s >> 24) & 15)); }
+    FILE* f = fopen(argv[4], "wb"); fwrite(img.data(), 1, img.size(), f); fclose(f);
+    crtcli::write_png_rgba8(argv[3], img.data(), w, h);
+    return 0;
+}
+''')
+    exe = tmp_path / "png_main"
+    csrc = os.path.join(ROOT, "cudart_b200", "csrc")
+    libdir = os.path.join(ROOT, "cudart_b200")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", csrc, str(src), os.path.join(csrc, "cli", "scene_io.cpp"), "-o", str(exe),
+                    "-L", libdir, "-lcrt_b200", "-lz", "-lpthread", "-Wl,-rpath," + libdir], check=True)
+    for w, h in ((1, 1), (40, 30), (640, 480), (1920, 1080), (7, 5000), (70000, 3)):
+        png, raw = tmp_path / "o.png", tmp_path / "o.raw"
+        subprocess.run([str(exe), str(w), str(h), str(png), str(raw)], check=True)
+        data = png.read_bytes()
+        assert data[:8] == b"\x89PNG\r\n\x1a\n"
+        off, idat, tags = 8, b"", []
+        while off < len(data):
+            n, tag = struct.unpack(">I4s", data[off:off + 8])
+            body = data[off + 8:off + 8 + n]
+            assert zlib.crc32(tag + body) == struct.unpack(">I", data[off + 8 + n:off + 12 + n])[0]
+            tags.append(tag)
+            if tag == b"IHDR":
+                assert struct.unpack(">IIBBBBB", body) == (w, h, 8, 6, 0, 0, 0)
+            if tag == b"IDAT":
+                idat += body
+            off += 12 + n
+        assert tags == [b"IHDR", b"IDAT", b"IEND"]
+        rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 4 * w)        # checks the combined Adler-32
+        assert (rows[:, 0] == 0).all()
+        assert np.array_equal(rows[:, 1:], np.frombuffer(raw.read_bytes(), np.uint8).reshape(h, 4 * w))
+        if shutil.which("taskset"):
+            subprocess.run(["taskset", "-c", "0", str(exe), str(w), str(h), str(tmp_path / "one.png"), str(raw)], check=True)
+            assert (tmp_path / "one.png").read_bytes() == data
