@@ -229,3 +229,70 @@ int main(int argc, char** argv) {
         if shutil.which("taskset"):
             subprocess.run(["taskset", "-c", "0", str(exe), str(w), str(h), str(tmp_path / "one.png"), str(raw)], check=True)
             assert (tmp_path / "one.png").read_bytes() == data
+
+
+def test_fast_obj_lines_random_near_misses(tmp_path):
+    """Randomised version of the test above: vertex / normal / texture / face lines assembled from well-formed and
+    slightly malformed pieces (random blanks, tabs, signs, exponents, long digit strings, empty index fields, indices around
+    the valid range).  Whatever the reference parser's rules make of each file - a scene or an error - the fast path must
+    make the same of it."""
+    import random
+    rng = random.Random(20261018)
+
+    def number():
+        k = rng.random()
+        if k < 0.55:
+            return "%.6f" % rng.uniform(-50, 50)
+        if k < 0.65:
+            return str(rng.randint(-9, 9))
+        if k < 0.72:
+            return "%.3e" % rng.uniform(-1e3, 1e3)
+        if k < 0.76:
+            return rng.choice(["-0", "0.000000", "-0.000000", "+1.5", ".5", "5.", "1e-45", "1e39", "1e-39", "0x10", "nan", "inf", "1.5f", "1,5", ""])
+        return "%.9g" % rng.uniform(-1e-3, 1e-3)
+
+    def sep():
+        return " " if rng.random() < 0.93 else rng.choice(["  ", "\t", " \t"])
+
+    def index(n):
+        k = rng.random()
+        if k < 0.8:
+            return str(rng.randint(1, max(n, 1)))
+        if k < 0.88:
+            return str(-rng.randint(1, max(n, 1)))
+        return rng.choice(["0", str(n + 1), str(-n - 1), "0000000002", "12345678901", "", "1x", "+1"])
+
+    loaded = failed = 0
+    for case in range(40):
+        nv, nn, nt = rng.randint(3, 12), rng.randint(1, 4), rng.randint(1, 4)
+        # mostly clean files (so that a good share loads), a few with several near misses
+        dirty = 0.0 if case % 3 == 0 else (0.02 if case % 3 == 1 else 0.15)
+
+        def maybe(clean, messy):
+            return messy() if rng.random() < dirty else clean
+
+        out = ["mtllib quirky.mtl", "o first", "usemtl red"]
+        for _ in range(nv):
+            out.append("v" + maybe(" ", sep) + maybe(" ", sep).join(maybe("%.6f" % rng.uniform(-5, 5), number) for _ in range(3)) + maybe("", lambda: rng.choice([" ", "\t", " 1.0"])))
+        for _ in range(nn):
+            out.append("vn " + " ".join(maybe("%.4f" % rng.uniform(-1, 1), number) for _ in range(3)))
+        for _ in range(nt):
+            out.append("vt " + " ".join(maybe("%.4f" % rng.uniform(0, 1), number) for _ in range(rng.choice([2, 2, 3]))))
+        for f in range(rng.randint(2, 10)):
+            form = rng.choice(["v", "v/t", "v//n", "v/t/n"])
+            corners = []
+            for _ in range(3 if rng.random() > dirty / 3 else rng.choice([2, 4])):
+                v, t, n = maybe(str(rng.randint(1, nv)), lambda: index(nv)), maybe(str(rng.randint(1, nt)), lambda: index(nt)), maybe(str(rng.randint(1, nn)), lambda: index(nn))
+                corners.append({"v": v, "v/t": v + "/" + t, "v//n": v + "//" + n, "v/t/n": v + "/" + t + "/" + n}[form] + maybe("", lambda: rng.choice(["/", "//"])))
+            out.append("f" + maybe(" ", sep) + maybe(" ", sep).join(corners) + maybe("", lambda: " "))
+            if f == 3:
+                out += ["g second", "usemtl green"]
+        text = "\n".join(out) + ("\n" if rng.random() < 0.8 else "")
+        d = tmp_path / ("case%d" % case)
+        d.mkdir()
+        fast, slow = _run_both_parsers(d, _quirky_assets(d, text, crlf=(case % 13 == 5)))
+        assert fast[:3] == slow[:3], (case, text, fast[:3], slow[:3])
+        assert fast[3] == slow[3], (case, text)
+        loaded += fast[0] == 0
+        failed += fast[0] != 0
+    assert loaded >= 8 and failed >= 8, (loaded, failed)
