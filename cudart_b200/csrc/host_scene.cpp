@@ -51,6 +51,28 @@ inline uint32_t fork_min() {
     return v;
 }
 constexpr int kForkLevels = 4;
+// Above the forks only one thread (then two, four, eight) works on a whole range: the top levels scan their range - bounds,
+// bins - in kScanChunks contiguous chunks on threads of their own and fold the chunk results IN ORDER with the same
+// min / max the sequential scan uses.  `a < b ? a : b` keeps the LAST of several equal minima (that is what tells -0 from
+// +0), and folding chunk results in order keeps the last chunk's last one, so for finite coordinates the result has the
+// bits of the sequential scan whatever the chunking; the builders fall back to the sequential scan when a coordinate is not
+// finite (a NaN does not fold that way).  The chunk count is fixed, not the machine's.
+constexpr uint32_t kScanChunks = 16;
+inline uint32_t scan_min() { return 8 * fork_min(); }          // ranges of >= 131 072 primitives by default
+template <class F>
+void chunked(uint32_t lo, uint32_t hi, F fn) {                  // fn(chunk, begin, end)
+    const uint64_t n = hi - lo;
+    auto bound = [=](uint32_t c) { return lo + (uint32_t)(n * c / kScanChunks); };
+    std::vector<std::unique_ptr<Worker>> th;
+    for (uint32_t c = 1; c < kScanChunks; c++) th.emplace_back(new Worker([=, &fn] { fn(c, bound(c), bound(c + 1)); }));
+    std::exception_ptr first;
+    try { fn(0u, bound(0), bound(1)); } catch (...) { first = std::current_exception(); }
+    for (auto& t : th) {
+        try { t->join(); } catch (...) { if (!first) first = std::current_exception(); }
+    }
+    if (first) std::rethrow_exception(first);
+}
+inline bool finite3(const F3& v) { return std::isfinite(v.x) && std::isfinite(v.y) && std::isfinite(v.z); }
 
 struct FreeDeleter { void operator()(void* p) const { std::free(p); } };
 template <class T>
@@ -595,8 +617,8 @@ namespace {
 struct TightPrim { uint32_t first, count; F3 mn, mx, c; };     // members[first .. first + count)
 
 struct TightBuilder {
-    std::vector<TightPrim> prims;
-    std::vector<uint32_t> members;               // triangle indices, grouped per primitive
+    RawVec<TightPrim> prims;
+    RawVec<uint32_t> members;                    // triangle indices, grouped per primitive
     std::vector<uint32_t> order;                 // tight slot -> original triangle index
     // Large subtrees are built on their own threads (disjoint primitive ranges): nodes come from a pre-sized pool
     // through an atomic counter, a leaf's slots are known from the weight in front of it, and place() writes the pool
@@ -611,10 +633,21 @@ struct TightBuilder {
     // measured monkeys 1189 -> 1226, 1M terrain 602 -> 606 Msamples/s, but cornellSphere (static) 2266 -> 2048
     // (profiles/r02n_tuning_sweep.jsonl).
     uint32_t max_leaf = 8;
+    bool finite = false;                         // every primitive box is finite: the top levels may scan in chunks
 
     void run() {
         uint32_t total = 0;
         for (const TightPrim& p : prims) total += p.count;
+        {
+            std::atomic<bool> ok{true};
+            const TightPrim* const pp = prims.data();
+            parallel_for((uint32_t)prims.size(), [&ok, pp](uint32_t b, uint32_t e) {
+                bool f = true;
+                for (uint32_t i = b; i < e; i++) f = f && finite3(pp[i].mn) && finite3(pp[i].mx) && finite3(pp[i].c);
+                if (!f) ok = false;
+            });
+            finite = ok;
+        }
         pool = raw_array<Node>(2 * prims.size() + 2);
         order.assign(total, 0u);
         next_node = 0;
@@ -653,14 +686,32 @@ struct TightBuilder {
     }
     uint32_t build(uint32_t lo, uint32_t hi, uint32_t slot_base, int depth) {
         const uint32_t my = next_node.fetch_add(1);
-        F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}, cmn = mn, cmx = mx;
-        uint32_t weight = 0;
-        for (uint32_t i = lo; i < hi; i++) {
-            mn = lo3(mn, prims[i].mn); mx = hi3(mx, prims[i].mx);
-            cmn = lo3(cmn, prims[i].c); cmx = hi3(cmx, prims[i].c);
-            weight += prims[i].count;
-        }
         const uint32_t n = hi - lo;
+        const bool in_chunks = finite && depth < kForkLevels && n >= scan_min();
+        struct Bounds { F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}, cmn{FLT_MAX, FLT_MAX, FLT_MAX}, cmx{-FLT_MAX, -FLT_MAX, -FLT_MAX}; uint32_t weight = 0; };
+        auto scan_bounds = [this](uint32_t a, uint32_t b) {
+            Bounds r;
+            for (uint32_t i = a; i < b; i++) {
+                r.mn = lo3(r.mn, prims[i].mn); r.mx = hi3(r.mx, prims[i].mx);
+                r.cmn = lo3(r.cmn, prims[i].c); r.cmx = hi3(r.cmx, prims[i].c);
+                r.weight += prims[i].count;
+            }
+            return r;
+        };
+        Bounds all;
+        if (in_chunks) {
+            Bounds part[kScanChunks];
+            chunked(lo, hi, [&](uint32_t c, uint32_t a, uint32_t b) { part[c] = scan_bounds(a, b); });
+            for (const Bounds& r : part) {
+                all.mn = lo3(all.mn, r.mn); all.mx = hi3(all.mx, r.mx);
+                all.cmn = lo3(all.cmn, r.cmn); all.cmx = hi3(all.cmx, r.cmx);
+                all.weight += r.weight;
+            }
+        } else {
+            all = scan_bounds(lo, hi);
+        }
+        const F3 mn = all.mn, mx = all.mx, cmn = all.cmn, cmx = all.cmx;
+        const uint32_t weight = all.weight;
         auto make_leaf = [&]() {
             Node& nd = pool[my];
             nd.mn = mn; nd.mx = mx;
@@ -688,7 +739,8 @@ struct TightBuilder {
         if (n == 1 || (leaf_ok && weight <= 2)) return make_leaf();
         constexpr int kBins = 16;
         // the bins of all three axes in ONE pass over the primitives (an axis without extent gets none)
-        struct Bin { F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}; uint32_t w = 0; } bins[3][kBins];
+        struct Bin { F3 mn{FLT_MAX, FLT_MAX, FLT_MAX}, mx{-FLT_MAX, -FLT_MAX, -FLT_MAX}; uint32_t w = 0; };
+        struct Bins { Bin b[3][kBins]; };
         float c0s[3], scales[3];
         bool use[3];
         for (int ax = 0; ax < 3; ax++) {
@@ -697,18 +749,36 @@ struct TightBuilder {
             c0s[ax] = c0;
             scales[ax] = use[ax] ? kBins / (c1 - c0) : 0.f;
         }
-        for (uint32_t i = lo; i < hi; i++) {
-            const TightPrim& p = prims[i];
-            const float cc[3] = {p.c.x, p.c.y, p.c.z};
-            for (int ax = 0; ax < 3; ax++) {
-                if (!use[ax]) continue;
-                int b = (int)((cc[ax] - c0s[ax]) * scales[ax]);
-                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-                Bin& bn = bins[ax][b];
-                bn.mn = lo3(bn.mn, p.mn); bn.mx = hi3(bn.mx, p.mx);
-                bn.w += p.count;
+        auto scan_bins = [&](Bins& out_bins, uint32_t a, uint32_t b_end) {
+            for (uint32_t i = a; i < b_end; i++) {
+                const TightPrim& p = prims[i];
+                const float cc[3] = {p.c.x, p.c.y, p.c.z};
+                for (int ax = 0; ax < 3; ax++) {
+                    if (!use[ax]) continue;
+                    int b = (int)((cc[ax] - c0s[ax]) * scales[ax]);
+                    b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                    Bin& bn = out_bins.b[ax][b];
+                    bn.mn = lo3(bn.mn, p.mn); bn.mx = hi3(bn.mx, p.mx);
+                    bn.w += p.count;
+                }
             }
+        };
+        Bins binned;
+        if (in_chunks) {
+            std::unique_ptr<Bins[]> part(new Bins[kScanChunks]);
+            chunked(lo, hi, [&](uint32_t c, uint32_t a, uint32_t b) { scan_bins(part[c], a, b); });
+            for (uint32_t c = 0; c < kScanChunks; c++)
+                for (int ax = 0; ax < 3; ax++)
+                    for (int b = 0; b < kBins; b++) {
+                        Bin& bn = binned.b[ax][b];
+                        const Bin& r = part[c].b[ax][b];
+                        bn.mn = lo3(bn.mn, r.mn); bn.mx = hi3(bn.mx, r.mx);
+                        bn.w += r.w;
+                    }
+        } else {
+            scan_bins(binned, lo, hi);
         }
+        const auto& bins = binned.b;
         int bestAxis = -1, bestSplit = 0;
         double bestCost = DBL_MAX;
         for (int ax = 0; ax < 3; ax++) {
@@ -824,20 +894,10 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
     if (n_tris == 0) return;
     out.boxes.assign(6 * (size_t)n_tris, 0.f);
     TightBuilder tb, ub;                    // bounded primitives / groups of triangles without a distance bound
-    tb.prims.reserve(n_tris);
-    tb.members.reserve(n_tris);
     std::vector<uint32_t> leaf_of(n_tris, 0xffffffffu);
     auto set_box = [&](uint32_t i, const F3& mn, const F3& mx) {
         float* b = &out.boxes[6 * (size_t)i];
         b[0] = mn.x; b[1] = mn.y; b[2] = mn.z; b[3] = mx.x; b[4] = mx.y; b[5] = mx.z;
-    };
-    auto add_prim = [](TightBuilder& bd, const std::vector<uint32_t>& m, const F3& mn, const F3& mx) {
-        TightPrim pr;
-        pr.first = (uint32_t)bd.members.size(); pr.count = (uint32_t)m.size();
-        pr.mn = mn; pr.mx = mx;
-        pr.c = {(mn.x + mx.x) * 0.5f, (mn.y + mx.y) * 0.5f, (mn.z + mx.z) * 0.5f};
-        bd.members.insert(bd.members.end(), m.begin(), m.end());
-        bd.prims.push_back(pr);
     };
     // the per-triangle bound is the expensive part (double precision, square roots): all host threads
     std::vector<F3> infl_mn(n_tris), infl_mx(n_tris);
@@ -869,53 +929,118 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
         if (out.dynamic_pad) { infl_mn.swap(tight_mn); infl_mx.swap(tight_mx); }
         tb.max_leaf = ub.max_leaf = out.dynamic_pad ? 4 : 8;
     }
-    std::vector<uint32_t> bounded, unbounded, one(1);
-    std::vector<F3> bmn, bmx;
-    for (uint32_t k = 0; k < n_ref_nodes; k++) {
-        const RefNode& lf = ref_nodes[k];
-        if (lf.nTris <= 0) continue;
-        // The leaf's own box in min/max order (the reference's slab test sorts each axis, renderer.cu:339-343); a box that
-        // is not finite is replaced by the region: the gate in the kernel stays the exact reference box either way.
-        F3 gmn = lo3(lf.mn, lf.mx), gmx = hi3(lf.mn, lf.mx);
-        const float gb[6] = {gmn.x, gmn.y, gmn.z, gmx.x, gmx.y, gmx.z};
-        bool finite = true;
-        for (float f : gb) finite = finite && std::isfinite(f);
-        if (!finite) { gmn = region_lo; gmx = region_hi; }
-        bounded.clear(); unbounded.clear(); bmn.clear(); bmx.clear();
-        double split_cost = 0;
-        for (uint32_t i = 0; i < (uint32_t)(uint16_t)lf.nTris && (uint32_t)lf.offset + i < n_tris; i++) {
-            const uint32_t idx = (uint32_t)lf.offset + i;
-            // a triangle claimed by two leaves (not a tree the reference builds) is reachable through either box: the gate
-            // could not say which, so such input keeps the reference-leaf tree only
-            if (leaf_of[idx] != 0xffffffffu) { out = TightBvh(); return; }
-            leaf_of[idx] = k;
-            const F3 mn = infl_mn[idx], mx = infl_mx[idx];
-            if (infl_ok[idx]) {
-                bounded.push_back(idx); bmn.push_back(mn); bmx.push_back(mx);
-                split_cost += TightBuilder::area(mn, mx);
+    // One pass over the reference's leaves decides, per leaf, between individually boxed triangles and the leaf kept whole.
+    // The leaves are independent, so contiguous ranges of them are processed on the host's threads into lists of their own
+    // that are concatenated in leaf order afterwards: the same primitive lists as one sequential pass.
+    struct LeafChunk {
+        std::vector<TightPrim> tb_prims, ub_prims;           // `first` relative to this chunk's member lists
+        std::vector<uint32_t> tb_members, ub_members;
+        uint32_t n_split = 0, n_unbounded = 0;
+    };
+    const uint32_t n_chunks = n_ref_nodes < (1u << 15) ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<LeafChunk> chunks(n_chunks);
+    uint32_t claimed_twice = 0;                               // set (atomically) when two leaves claim one triangle
+    uint32_t* const leaf_idx = leaf_of.data();
+    auto leaf_pass = [&](LeafChunk& ch, uint32_t k_begin, uint32_t k_end) {
+        auto add = [](std::vector<TightPrim>& prims, std::vector<uint32_t>& members, const uint32_t* m, size_t n, const F3& mn, const F3& mx) {
+            TightPrim pr;
+            pr.first = (uint32_t)members.size(); pr.count = (uint32_t)n;
+            pr.mn = mn; pr.mx = mx;
+            pr.c = {(mn.x + mx.x) * 0.5f, (mn.y + mx.y) * 0.5f, (mn.z + mx.z) * 0.5f};
+            members.insert(members.end(), m, m + n);
+            prims.push_back(pr);
+        };
+        std::vector<uint32_t> bounded, unbounded;
+        std::vector<F3> bmn, bmx;
+        for (uint32_t k = k_begin; k < k_end; k++) {
+            const RefNode& lf = ref_nodes[k];
+            if (lf.nTris <= 0) continue;
+            // The leaf's own box in min/max order (the reference's slab test sorts each axis, renderer.cu:339-343); a box
+            // that is not finite is replaced by the region: the gate in the kernel stays the exact reference box either way.
+            F3 gmn = lo3(lf.mn, lf.mx), gmx = hi3(lf.mn, lf.mx);
+            const float gb[6] = {gmn.x, gmn.y, gmn.z, gmx.x, gmx.y, gmx.z};
+            bool finite = true;
+            for (float f : gb) finite = finite && std::isfinite(f);
+            if (!finite) { gmn = region_lo; gmx = region_hi; }
+            bounded.clear(); unbounded.clear(); bmn.clear(); bmx.clear();
+            double split_cost = 0;
+            bool duplicate = false;
+            for (uint32_t i = 0; i < (uint32_t)(uint16_t)lf.nTris && (uint32_t)lf.offset + i < n_tris; i++) {
+                const uint32_t idx = (uint32_t)lf.offset + i;
+                // a triangle claimed by two leaves (not a tree the reference builds) is reachable through either box: the
+                // gate could not say which, so such input keeps the reference-leaf tree only
+                if (__atomic_exchange_n(&leaf_idx[idx], k, __ATOMIC_RELAXED) != 0xffffffffu) { duplicate = true; break; }
+                const F3 mn = infl_mn[idx], mx = infl_mx[idx];
+                if (infl_ok[idx]) {
+                    bounded.push_back(idx); bmn.push_back(mn); bmx.push_back(mx);
+                    split_cost += TightBuilder::area(mn, mx);
+                } else {
+                    unbounded.push_back(idx);
+                    ch.n_unbounded++;
+                }
+            }
+            if (duplicate) { __atomic_store_n(&claimed_twice, 1u, __ATOMIC_RELAXED); return; }
+            if (!unbounded.empty()) {
+                add(ch.ub_prims, ch.ub_members, unbounded.data(), unbounded.size(), gmn, gmx);
+                for (uint32_t i : unbounded) set_box(i, gmn, gmx);
+            }
+            if (bounded.empty()) continue;
+            // Individually inflated triangles, or the whole leaf behind its exact box?  SAH: sum of the inflated areas (plus
+            // the extra nodes and gate tests, hence the 0.7) against the leaf area times its triangle count.
+            const double group_cost = TightBuilder::area(gmn, gmx) * (double)bounded.size();
+            if (split_cost < 0.7 * group_cost) {
+                for (size_t j = 0; j < bounded.size(); j++) {
+                    add(ch.tb_prims, ch.tb_members, &bounded[j], 1, bmn[j], bmx[j]);
+                    set_box(bounded[j], bmn[j], bmx[j]);
+                }
+                ch.n_split += (uint32_t)bounded.size();
             } else {
-                unbounded.push_back(idx);
-                out.n_unbounded++;
+                add(ch.tb_prims, ch.tb_members, bounded.data(), bounded.size(), gmn, gmx);
+                for (uint32_t i : bounded) set_box(i, gmn, gmx);
             }
         }
-        if (!unbounded.empty()) {
-            add_prim(ub, unbounded, gmn, gmx);
-            for (uint32_t i : unbounded) set_box(i, gmn, gmx);
+    };
+    if (n_chunks == 1) {
+        leaf_pass(chunks[0], 0, n_ref_nodes);
+    } else {
+        std::vector<std::unique_ptr<Worker>> th;
+        for (uint32_t p = 0; p < n_chunks; p++) {
+            const uint32_t kb = (uint32_t)((uint64_t)n_ref_nodes * p / n_chunks), ke = (uint32_t)((uint64_t)n_ref_nodes * (p + 1) / n_chunks);
+            th.emplace_back(new Worker([&, p, kb, ke] { leaf_pass(chunks[p], kb, ke); }));
         }
-        if (bounded.empty()) continue;
-        // Individually inflated triangles, or the whole leaf behind its exact box?  SAH: sum of the inflated areas (plus
-        // the extra nodes and gate tests, hence the 0.7) against the leaf area times its triangle count.
-        const double group_cost = TightBuilder::area(gmn, gmx) * (double)bounded.size();
-        if (split_cost < 0.7 * group_cost) {
-            for (size_t j = 0; j < bounded.size(); j++) {
-                one[0] = bounded[j];
-                add_prim(tb, one, bmn[j], bmx[j]);
-                set_box(bounded[j], bmn[j], bmx[j]);
-            }
-            out.n_split += (uint32_t)bounded.size();
+        std::exception_ptr first;
+        for (auto& t : th) {
+            try { t->join(); } catch (...) { if (!first) first = std::current_exception(); }
+        }
+        if (first) std::rethrow_exception(first);
+    }
+    if (__atomic_load_n(&claimed_twice, __ATOMIC_RELAXED)) { out = TightBvh(); return; }
+    {   // concatenate the chunks' lists in leaf order; every chunk copies its own part to its known place
+        std::vector<size_t> tbp(n_chunks + 1, 0), tbm(n_chunks + 1, 0), ubp(n_chunks + 1, 0), ubm(n_chunks + 1, 0);
+        for (uint32_t p = 0; p < n_chunks; p++) {
+            const LeafChunk& ch = chunks[p];
+            tbp[p + 1] = tbp[p] + ch.tb_prims.size(); tbm[p + 1] = tbm[p] + ch.tb_members.size();
+            ubp[p + 1] = ubp[p] + ch.ub_prims.size(); ubm[p + 1] = ubm[p] + ch.ub_members.size();
+            out.n_split += ch.n_split;
+            out.n_unbounded += ch.n_unbounded;
+        }
+        tb.prims.resize(tbp[n_chunks]); tb.members.resize(tbm[n_chunks]);
+        ub.prims.resize(ubp[n_chunks]); ub.members.resize(ubm[n_chunks]);
+        auto splice = [](TightBuilder& bd, const std::vector<TightPrim>& prims, const std::vector<uint32_t>& members, size_t prim_at, size_t member_at) {
+            TightPrim* dst = bd.prims.data() + prim_at;
+            for (size_t i = 0; i < prims.size(); i++) { dst[i] = prims[i]; dst[i].first += (uint32_t)member_at; }
+            if (!members.empty()) std::memcpy(bd.members.data() + member_at, members.data(), members.size() * sizeof(uint32_t));
+        };
+        auto splice_chunk = [&](uint32_t p) {
+            splice(tb, chunks[p].tb_prims, chunks[p].tb_members, tbp[p], tbm[p]);
+            splice(ub, chunks[p].ub_prims, chunks[p].ub_members, ubp[p], ubm[p]);
+        };
+        if (n_chunks == 1) {
+            splice_chunk(0);
         } else {
-            add_prim(tb, bounded, gmn, gmx);
-            for (uint32_t i : bounded) set_box(i, gmn, gmx);
+            std::vector<std::unique_ptr<Worker>> th;
+            for (uint32_t p = 0; p < n_chunks; p++) th.emplace_back(new Worker([&, p] { splice_chunk(p); }));
+            for (auto& t : th) t->join();
         }
     }
     if (tb.prims.empty() && ub.prims.empty()) { out = TightBvh(); return; }
@@ -948,7 +1073,6 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
     TightRecord* const recs = out.records.data();
     RefTriangle* const ttris = out.tris.data();
     const uint32_t* const ord = order.data();
-    const uint32_t* const leaf_idx = leaf_of.data();
     parallel_for(n_used, [=](uint32_t b, uint32_t e) {
         for (uint32_t slot = b; slot < e; slot++) {
             const uint32_t i = ord[slot];

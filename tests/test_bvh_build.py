@@ -125,6 +125,30 @@ def test_threaded_bvh_build_is_the_sequential_tree():
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
 
 
+def signed_zero_scene():
+    """3 200 triangles on a 40 x 40 grid whose coordinates are small integers and zeros of BOTH signs, many of them equal:
+    box minima / maxima with ties between -0 and +0 everywhere - the case where folding per-thread partial bounds in the wrong
+    order would change bits (host_scene.cpp `chunked`)."""
+    import dataclasses
+    from cudart_b200 import scenebuild
+    from cudart_b200.procedural import terrain_scene
+    from cudart_b200.scenefile import TRIANGLE_DTYPE
+    rng = np.random.default_rng(11)
+    n = 40
+    gx, gz = np.meshgrid(np.arange(n + 1), np.arange(n + 1))
+    V = np.stack([(gx.ravel() % 5 - 2).astype(np.float32), np.zeros((n + 1) ** 2, np.float32), (gz.ravel() % 7 - 3).astype(np.float32)], axis=1)
+    V[V == 0] = np.where(rng.random(int((V == 0).sum())) < 0.5, np.float32(-0.0), np.float32(0.0))
+    j, i = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    a = (j * (n + 1) + i).ravel()
+    idx = np.concatenate([np.stack([a, a + n + 1, a + 1], 1), np.stack([a + 1, a + n + 1, a + n + 2], 1)])
+    P = V[idx].reshape(-1, 9)
+    t = np.zeros(P.shape[0], TRIANGLE_DTYPE)
+    t["triId"] = np.arange(P.shape[0])
+    t["v1"], t["e1"], t["e2"] = P[:, 0:3], P[:, 3:6] - P[:, 0:3], P[:, 6:9] - P[:, 0:3]
+    tris, nodes = scenebuild.build_bvh(t, P)
+    return dataclasses.replace(terrain_scene(2, 16, 12), tris=tris, nodes=nodes)
+
+
 def _derived_fingerprints_in_subprocess(fork_min):
     """{scene: {pad mode: fingerprint}} of every host-derived array (crt_derived_fingerprint), computed in a fresh process with
     the fork threshold of the threaded builders forced to `fork_min`: the six golden scenes plus the 131 074-triangle terrain."""
@@ -140,8 +164,10 @@ def _derived_fingerprints_in_subprocess(fork_min):
         "from grazing import region_of\n"
         "from cudart_b200 import scenebuild, load_crts\n"
         "from cudart_b200.procedural import terrain_scene\n"
+        "from test_bvh_build import signed_zero_scene\n"
         "scenes = {name: load_crts(os.path.join(GOLDEN, name + '.crts.gz')) for name in SCENES}\n"
         "scenes['terrain256'] = terrain_scene(256, 64, 36)\n"
+        "scenes['signed_zeros'] = signed_zero_scene()\n"
         "out = {}\n"
         "for name, fs in scenes.items():\n"
         "    lo, hi = region_of(fs)\n"
