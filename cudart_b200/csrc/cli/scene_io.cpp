@@ -580,7 +580,7 @@ void write_png_rgba8(const std::string& path, const uint8_t* rgba, unsigned w, u
         }
     };
     {
-        const unsigned n_threads = std::min(n_bands, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+        const unsigned n_threads = std::min(n_bands, crt::host_threads());
         std::vector<std::unique_ptr<crt::Worker>> th;
         for (unsigned t = 1; t < n_threads; t++) th.emplace_back(new crt::Worker(work));
         work();

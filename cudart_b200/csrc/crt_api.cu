@@ -123,7 +123,7 @@ void fingerprint_mix(Fingerprint& fp, const void* data, size_t bytes) {
             fingerprint_mix_serial(part[c], (const unsigned char*)data + c * kChunk, std::min(kChunk, bytes - c * kChunk));
         }
     };
-    const size_t n_threads = std::min<size_t>(std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())), n_chunks);
+    const size_t n_threads = std::min<size_t>(host_threads(), n_chunks);
     std::vector<std::unique_ptr<Worker>> th;
     for (size_t t = 1; t < n_threads; t++) th.emplace_back(new Worker(work));
     work();

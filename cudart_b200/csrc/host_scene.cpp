@@ -937,7 +937,7 @@ void build_tight_bvh(const RefTriangle* tris, uint32_t n_tris, const RefNode* re
         std::vector<uint32_t> tb_members, ub_members;
         uint32_t n_split = 0, n_unbounded = 0;
     };
-    const uint32_t n_chunks = n_ref_nodes < (1u << 15) ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const uint32_t n_chunks = n_ref_nodes < (1u << 15) ? 1u : host_threads();
     std::vector<LeafChunk> chunks(n_chunks);
     uint32_t claimed_twice = 0;                               // set (atomically) when two leaves claim one triangle
     uint32_t* const leaf_idx = leaf_of.data();

@@ -6,6 +6,7 @@
 //  * flatten_wide(): that binary tree re-flattened into the 128-byte 4-ary node the kernels read.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <exception>
@@ -41,10 +42,21 @@ public:
     ~Worker() { if (t_.joinable()) t_.join(); }
 };
 
+// Host threads the builders and loaders use for one job: the machine's, at most 16; CRT_HOST_THREADS overrides it (1 .. 64).
+// Nothing they produce depends on this number (tests/test_bvh_build.py runs the derivation with 1, 3 and 16).
+inline uint32_t host_threads() {
+    static const uint32_t v = [] {
+        const char* e = getenv("CRT_HOST_THREADS");
+        const int forced = e ? atoi(e) : 0;
+        return forced > 0 ? (uint32_t)std::min(forced, 64) : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    }();
+    return v;
+}
+
 // fn(begin, end) over [0, n) in contiguous chunks on the host's threads (the chunks write disjoint outputs)
 template <class F>
 inline void parallel_for(uint32_t n, F fn) {
-    const uint32_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const uint32_t hw = host_threads();
     const uint32_t parts = n < (1u << 15) ? 1u : hw;
     if (parts == 1) { fn(0u, n); return; }
     std::vector<std::unique_ptr<Worker>> th;

@@ -149,7 +149,7 @@ def signed_zero_scene():
     return dataclasses.replace(terrain_scene(2, 16, 12), tris=tris, nodes=nodes)
 
 
-def _derived_fingerprints_in_subprocess(fork_min):
+def _derived_fingerprints_in_subprocess(fork_min, host_threads=None):
     """{scene: {pad mode: fingerprint}} of every host-derived array (crt_derived_fingerprint), computed in a fresh process with
     the fork threshold of the threaded builders forced to `fork_min`: the six golden scenes plus the 131 074-triangle terrain."""
     import json
@@ -173,7 +173,11 @@ def _derived_fingerprints_in_subprocess(fork_min):
         "    lo, hi = region_of(fs)\n"
         "    out[name] = {str(m): scenebuild.derived_fingerprint(fs.tris, fs.nodes, lo, hi, m) for m in (1, 2)}\n"
         "print('FP ' + json.dumps(out))\n" % (root, os.path.join(root, "tests")))
-    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CRT_BVH_FORK_MIN=str(fork_min)), capture_output=True, text=True)
+    env = dict(os.environ, CRT_BVH_FORK_MIN=str(fork_min))
+    env.pop("CRT_HOST_THREADS", None)
+    if host_threads:
+        env["CRT_HOST_THREADS"] = str(host_threads)       # chunk count of parallel_for and of the leaf pass (host_scene.h)
+    p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert p.returncode == 0, p.stderr[-2000:]
     return json.loads([l for l in p.stdout.splitlines() if l.startswith("FP ")][-1][3:])
 
@@ -185,4 +189,8 @@ def test_derived_arrays_do_not_depend_on_the_number_of_threads():
     switched off (threshold 2^30): the trees are functions of the input alone."""
     forced, default, off = (_derived_fingerprints_in_subprocess(m) for m in (8, 1 << 14, 1 << 30))
     assert forced == default == off
+    # ... nor on how many threads the per-element loops and the leaf pass are split over (the GPU box has 16 cores, this
+    # container 8)
+    for threads in (1, 3, 16):
+        assert _derived_fingerprints_in_subprocess(1 << 14, threads) == default, threads
     assert len({tuple(v["1"]) for v in forced.values()}) == len(forced)          # and the hash does tell the scenes apart
