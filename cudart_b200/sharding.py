@@ -1,7 +1,8 @@
 """Image-space sharding across the GPUs of one box: interleaved row tiles (tile k -> rank k % world), one
-process per GPU, ONE collective at the end (an all-gather of the compact per-rank accumulators over
-NCCL/NVLink), then de-interleave + resolve on the device.  The reference has no multi-GPU path at all
-(``main.cpp:155-162`` picks one device); the row-tile math here mirrors ``DTiling`` in ``csrc/kernels.cuh``.
+process per GPU, ONE exchange at read-out: every rank resolves its own tiles to RGBA8 on its GPU and rank 0
+collects them over NCCL/NVLink and de-interleaves (``gather_rgba8``, 4 bytes per pixel); the all-gather of the
+float4 accumulators (``gather_framebuffer``) stays for float parity checks.  The reference has no multi-GPU path
+at all (``main.cpp:155-162`` picks one device); the row-tile math here mirrors ``DTiling`` in ``csrc/kernels.cuh``.
 
 The path shards with no data-path exchange: pixels are independent and the RNG is keyed by the GLOBAL
 pixel index, so the image does not depend on ``world``.
